@@ -1,0 +1,253 @@
+// bands.cu -- one very large image split into row bands over several GPUs of one process
+// (BASELINE config 5: 32768 x 32768 RGB Sobel over 8 B200).
+//
+// Every device holds only its own band (RGB in, edge plane out).  The fused gray->Sobel kernel
+// needs one luma row above and below the band; the producer warp of the stencil kernel reads those
+// two RGB rows straight from the neighbouring device's band through the NVLink peer mapping
+// (cudaDeviceEnablePeerAccess), so there is no staging copy and no collective: the halo exchange
+// is fused into the kernel.  Where peer access is unavailable the two rows are copied with
+// cudaMemcpyPeerAsync into a local halo buffer first (same kernel, local pointers).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/ompimg_b200.h"
+#include "kernels.h"
+
+using namespace ompimg;
+
+namespace ompimg {
+
+__global__ void __launch_bounds__(256) synth2d_kernel(uint8_t *dst, size_t pitch, unsigned long long row_bytes, int rows, uint32_t seed,
+                                                      unsigned long long off) {
+    const unsigned long long total = row_bytes * rows;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long y = i / row_bytes, x = i - y * row_bytes;
+        const unsigned long long gi = off + i;
+        uint32_t v = seed + (uint32_t)(gi >> 2) * 0x9E3779B9u;
+        v ^= v >> 16; v *= 0x7feb352du; v ^= v >> 15; v *= 0x846ca68bu; v ^= v >> 16;
+        dst[y * pitch + x] = (uint8_t)(v >> (8 * (gi & 3)));
+    }
+}
+
+// sum of the bytes of a 2-D region (checksum of an edge plane's interior)
+__global__ void __launch_bounds__(256) byte_sum_kernel(const uint8_t *src, size_t pitch, int x0, int x1, int y0, int y1, unsigned long long *out) {
+    unsigned long long s = 0;
+    const long long wr = x1 - x0, total = wr * (long long)(y1 - y0);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long y = i / wr, x = i - y * wr;
+        s += src[(size_t)(y0 + y) * pitch + x0 + x];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+}  // namespace ompimg
+
+struct ompimg_bands {
+    int w, h, ch, ndev;
+    int dev[16];
+    int row0[17];
+    int sm_count[16];
+    size_t rpitch, epitch;
+    uint8_t *rgb[16];
+    uint8_t *edge[16];
+    uint8_t *halo[16];          // 2 rows (above, below) when peer access is unavailable
+    unsigned long long *sum[16];
+    bool direct[16][2];         // can device i read its (above, below) neighbour directly?
+    cudaStream_t st[16];
+    cudaEvent_t e0[16], e1[16];
+    int home;                   // device current before create()
+    char err[256];
+};
+
+#define BCK(call)                                                                                       \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            fprintf(stderr, "libompimg_b200: bands: %s failed: %s (%s:%d)\n", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return OMPIMG_ERR_CUDA;                                                                     \
+        }                                                                                               \
+    } while (0)
+
+extern "C" ompimg_bands *ompimg_bands_create(int w, int h, int ch, int ndev, const int *devices) {
+    if (w < 3 || h < 3 || !(ch == 1 || ch == 3 || ch == 4) || ndev < 1 || ndev > 16 || h < 2 * ndev) return nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return nullptr;
+    ompimg_bands *b = (ompimg_bands *)calloc(1, sizeof(ompimg_bands));
+    if (!b) return nullptr;
+    b->w = w; b->h = h; b->ch = ch; b->ndev = ndev;
+    cudaGetDevice(&b->home);
+    b->rpitch = ((size_t)w * ch + 127) / 128 * 128;
+    b->epitch = ((size_t)w + 127) / 128 * 128;
+    for (int i = 0; i <= ndev; ++i) b->row0[i] = (int)((long long)h * i / ndev);
+    bool ok = true;
+    for (int i = 0; i < ndev && ok; ++i) {
+        b->dev[i] = devices ? devices[i] : i % count;
+        if (b->dev[i] < 0 || b->dev[i] >= count) { ok = false; break; }
+        const int rows = b->row0[i + 1] - b->row0[i];
+        ok = cudaSetDevice(b->dev[i]) == cudaSuccess &&
+             cudaMalloc(&b->rgb[i], b->rpitch * rows) == cudaSuccess &&
+             cudaMalloc(&b->edge[i], b->epitch * rows) == cudaSuccess &&
+             cudaMalloc(&b->halo[i], 2 * b->rpitch) == cudaSuccess &&
+             cudaMalloc(&b->sum[i], 8) == cudaSuccess &&
+             cudaMemset(b->edge[i], 0, b->epitch * rows) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&b->st[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreate(&b->e0[i]) == cudaSuccess && cudaEventCreate(&b->e1[i]) == cudaSuccess &&
+             cudaDeviceGetAttribute(&b->sm_count[i], cudaDevAttrMultiProcessorCount, b->dev[i]) == cudaSuccess;
+    }
+    for (int i = 0; i < ndev && ok; ++i) {
+        cudaSetDevice(b->dev[i]);
+        for (int side = 0; side < 2; ++side) {
+            const int j = side == 0 ? i - 1 : i + 1;
+            b->direct[i][side] = false;
+            if (j < 0 || j >= ndev) continue;
+            if (b->dev[j] == b->dev[i]) { b->direct[i][side] = true; continue; }
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, b->dev[i], b->dev[j]) == cudaSuccess && can) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(b->dev[j], 0);
+                if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) b->direct[i][side] = true;
+                cudaGetLastError();
+            }
+        }
+    }
+    cudaSetDevice(b->home);
+    if (!ok) { ompimg_bands_destroy(b); return nullptr; }
+    return b;
+}
+
+extern "C" int ompimg_bands_destroy(ompimg_bands *b) {
+    if (!b) return OMPIMG_OK;
+    for (int i = 0; i < b->ndev; ++i) {
+        cudaSetDevice(b->dev[i]);
+        if (b->st[i]) { cudaStreamSynchronize(b->st[i]); cudaStreamDestroy(b->st[i]); }
+        if (b->e0[i]) cudaEventDestroy(b->e0[i]);
+        if (b->e1[i]) cudaEventDestroy(b->e1[i]);
+        cudaFree(b->rgb[i]); cudaFree(b->edge[i]); cudaFree(b->halo[i]); cudaFree(b->sum[i]);
+    }
+    cudaGetLastError();
+    cudaSetDevice(b->home);
+    free(b);
+    return OMPIMG_OK;
+}
+
+extern "C" int ompimg_bands_rows(const ompimg_bands *b, int i, int *row0, int *nrows) {
+    if (!b || i < 0 || i >= b->ndev) return OMPIMG_ERR_ARG;
+    if (row0) *row0 = b->row0[i];
+    if (nrows) *nrows = b->row0[i + 1] - b->row0[i];
+    return OMPIMG_OK;
+}
+
+static int bands_sync(ompimg_bands *b) {
+    for (int i = 0; i < b->ndev; ++i) { BCK(cudaSetDevice(b->dev[i])); BCK(cudaStreamSynchronize(b->st[i])); }
+    BCK(cudaSetDevice(b->home));
+    return OMPIMG_OK;
+}
+
+extern "C" int ompimg_bands_synth(ompimg_bands *b, unsigned int seed) {
+    if (!b) return OMPIMG_ERR_ARG;
+    const unsigned long long row = (unsigned long long)b->w * b->ch;
+    for (int i = 0; i < b->ndev; ++i) {
+        BCK(cudaSetDevice(b->dev[i]));
+        const int rows = b->row0[i + 1] - b->row0[i];
+        const unsigned long long off = row * b->row0[i];
+        if (b->rpitch == row) BCK(launch_synth(b->rgb[i], row * rows, seed, off, b->sm_count[i], b->st[i]));
+        else {
+            count_launch();
+            synth2d_kernel<<<b->sm_count[i] * 8, 256, 0, b->st[i]>>>(b->rgb[i], b->rpitch, row, rows, seed, off);
+            BCK(cudaGetLastError());
+        }
+    }
+    return bands_sync(b);
+}
+
+extern "C" int ompimg_bands_upload(ompimg_bands *b, const uint8_t *rgb_host) {
+    if (!b || !rgb_host) return OMPIMG_ERR_ARG;
+    const size_t row = (size_t)b->w * b->ch;
+    for (int i = 0; i < b->ndev; ++i) {
+        BCK(cudaSetDevice(b->dev[i]));
+        BCK(cudaMemcpy2DAsync(b->rgb[i], b->rpitch, rgb_host + row * b->row0[i], row, row, b->row0[i + 1] - b->row0[i],
+                              cudaMemcpyHostToDevice, b->st[i]));
+    }
+    return bands_sync(b);
+}
+
+extern "C" int ompimg_bands_rgb_to_edge(ompimg_bands *b, float *ms_max) {
+    if (!b) return OMPIMG_ERR_ARG;
+    const int mode = ompimg_get_luma_mode();
+    for (int i = 0; i < b->ndev; ++i) {
+        BCK(cudaSetDevice(b->dev[i]));
+        const int rows = b->row0[i + 1] - b->row0[i];
+        BCK(cudaEventRecord(b->e0[i], b->st[i]));
+        const uint8_t *above = nullptr, *below = nullptr;
+        if (i > 0) {
+            const uint8_t *peer_row = b->rgb[i - 1] + (size_t)(b->row0[i] - b->row0[i - 1] - 1) * b->rpitch;
+            if (b->direct[i][0]) above = peer_row;
+            else { BCK(cudaMemcpyPeerAsync(b->halo[i], b->dev[i], peer_row, b->dev[i - 1], b->rpitch, b->st[i])); above = b->halo[i]; }
+        }
+        if (i + 1 < b->ndev) {
+            const uint8_t *peer_row = b->rgb[i + 1];
+            if (b->direct[i][1]) below = peer_row;
+            else { BCK(cudaMemcpyPeerAsync(b->halo[i] + b->rpitch, b->dev[i], peer_row, b->dev[i + 1], b->rpitch, b->st[i])); below = b->halo[i] + b->rpitch; }
+        }
+        StencilArgs a{};
+        a.src = b->rgb[i]; a.dst = b->edge[i]; a.src_pitch = b->rpitch; a.dst_pitch = b->epitch;
+        a.width = b->w; a.height = rows; a.channels = b->ch; a.nframes = 1; a.fma_mode = mode;
+        a.halo_above = above; a.halo_below = below;
+        BCK(launch_sobel(a, b->sm_count[i], b->st[i]));
+        BCK(cudaEventRecord(b->e1[i], b->st[i]));
+    }
+    float mx = 0.f;
+    for (int i = 0; i < b->ndev; ++i) {
+        BCK(cudaSetDevice(b->dev[i]));
+        BCK(cudaEventSynchronize(b->e1[i]));
+        float ms = 0.f;
+        BCK(cudaEventElapsedTime(&ms, b->e0[i], b->e1[i]));
+        if (ms > mx) mx = ms;
+    }
+    BCK(cudaSetDevice(b->home));
+    if (ms_max) *ms_max = mx;
+    return OMPIMG_OK;
+}
+
+extern "C" int ompimg_bands_download_edge(ompimg_bands *b, uint8_t *edge_host) {
+    if (!b || !edge_host) return OMPIMG_ERR_ARG;
+    for (int i = 0; i < b->ndev; ++i) {
+        BCK(cudaSetDevice(b->dev[i]));
+        int y0 = b->row0[i], y1 = b->row0[i + 1];
+        if (y0 < 1) y0 = 1;
+        if (y1 > b->h - 1) y1 = b->h - 1;
+        if (y1 <= y0) continue;
+        BCK(cudaMemcpy2DAsync(edge_host + (size_t)y0 * b->w + 1, b->w, b->edge[i] + (size_t)(y0 - b->row0[i]) * b->epitch + 1, b->epitch,
+                              b->w - 2, y1 - y0, cudaMemcpyDeviceToHost, b->st[i]));
+    }
+    return bands_sync(b);
+}
+
+extern "C" int ompimg_bands_checksum(ompimg_bands *b, unsigned long long *sum) {
+    if (!b || !sum) return OMPIMG_ERR_ARG;
+    unsigned long long total = 0;
+    for (int i = 0; i < b->ndev; ++i) {
+        BCK(cudaSetDevice(b->dev[i]));
+        int y0 = b->row0[i], y1 = b->row0[i + 1];
+        if (y0 < 1) y0 = 1;
+        if (y1 > b->h - 1) y1 = b->h - 1;
+        BCK(cudaMemsetAsync(b->sum[i], 0, 8, b->st[i]));
+        if (y1 > y0) {
+            count_launch();
+            byte_sum_kernel<<<b->sm_count[i] * 8, 256, 0, b->st[i]>>>(b->edge[i], b->epitch, 1, b->w - 1, y0 - b->row0[i], y1 - b->row0[i], b->sum[i]);
+            BCK(cudaGetLastError());
+        }
+    }
+    for (int i = 0; i < b->ndev; ++i) {
+        BCK(cudaSetDevice(b->dev[i]));
+        unsigned long long s = 0;
+        BCK(cudaMemcpyAsync(&s, b->sum[i], 8, cudaMemcpyDeviceToHost, b->st[i]));
+        BCK(cudaStreamSynchronize(b->st[i]));
+        total += s;
+    }
+    BCK(cudaSetDevice(b->home));
+    *sum = total;
+    return OMPIMG_OK;
+}

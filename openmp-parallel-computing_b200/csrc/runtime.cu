@@ -1,0 +1,620 @@
+// runtime.cu -- the C ABI of libompimg_b200 (include/ompimg_b200.h): context, streams, pinned and
+// device memory, timers, the device-resident entry points, the host-buffer pipelines and the two
+// frozen reference prototypes.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/ompimg_b200.h"
+#include "kernels.h"
+
+namespace ompimg {
+std::atomic<long long> g_launch_count{0};
+}
+using namespace ompimg;
+
+namespace {
+
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    bool used = false;
+};
+
+struct DevBuf {   // grow-only device scratch
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct Ctx {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    int luma_mode = OMPIMG_LUMA_STRICT;
+    cudaStream_t streams[OMPIMG_NUM_STREAMS] = {};
+    cudaEvent_t edge_events[OMPIMG_NUM_STREAMS] = {};
+    std::vector<Timer> timers;
+    DevBuf scratch[4];                       // host-API staging on the device
+    DevBuf slots[OMPIMG_NUM_STREAMS][2];     // per-stream (input, output) slots of the batch pipeline
+    std::recursive_mutex mu;
+};
+Ctx g;
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    if (getenv("OMPIMG_VERBOSE")) fprintf(stderr, "[ompimg_b200] error: %s\n", g_err);
+    return code;
+}
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(OMPIMG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define NEED(cond, what)                                                    \
+    do {                                                                    \
+        if (!(cond)) return fail(OMPIMG_ERR_ARG, "invalid argument: %s", what); \
+    } while (0)
+
+int ensure_init() {
+    if (g.ready) {
+        cudaError_t e = cudaSetDevice(g.device);   // the binding is per host thread
+        if (e != cudaSuccess) return fail(OMPIMG_ERR_CUDA, "cudaSetDevice(%d): %s", g.device, cudaGetErrorString(e));
+        return OMPIMG_OK;
+    }
+    const char *d = getenv("OMPIMG_DEVICE");
+    return ompimg_init(d ? atoi(d) : 0);
+}
+#define INIT()                       \
+    do {                             \
+        int rc_ = ensure_init();     \
+        if (rc_ != OMPIMG_OK) return rc_; \
+    } while (0)
+
+int stream_of(int s, cudaStream_t *out) {
+    if (s < 0 || s >= OMPIMG_NUM_STREAMS) return fail(OMPIMG_ERR_ARG, "stream index %d out of range", s);
+    *out = g.streams[s];
+    return OMPIMG_OK;
+}
+#define STREAM(s, var)                      \
+    cudaStream_t var;                       \
+    do {                                    \
+        int rc_ = stream_of((s), &var);     \
+        if (rc_ != OMPIMG_OK) return rc_;   \
+    } while (0)
+
+int reserve(DevBuf &b, size_t bytes) {
+    if (b.cap >= bytes) return OMPIMG_OK;
+    if (b.p) { CK(cudaDeviceSynchronize()); CK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    const size_t want = (bytes + (1 << 20) - 1) & ~(size_t)((1 << 20) - 1);
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { b.p = nullptr; return fail(OMPIMG_ERR_NOMEM, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e)); }
+    b.cap = want;
+    return OMPIMG_OK;
+}
+#define RESERVE(buf, bytes)                  \
+    do {                                     \
+        int rc_ = reserve((buf), (bytes));   \
+        if (rc_ != OMPIMG_OK) return rc_;    \
+    } while (0)
+
+inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+bool is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// Pageable caller memory: pin it for the duration of one call when that pays (env OMPIMG_PIN=register),
+// default is to let cudaMemcpyAsync stage it.
+struct ScopedPin {
+    void *p = nullptr;
+    ScopedPin(const void *ptr, size_t bytes) {
+        const char *m = getenv("OMPIMG_PIN");
+        if (m && !strcmp(m, "register") && !is_pinned(ptr)) {
+            if (cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterDefault) == cudaSuccess) p = const_cast<void *>(ptr);
+            else cudaGetLastError();
+        }
+    }
+    ~ScopedPin() { if (p) cudaHostUnregister(p); }
+};
+
+}  // namespace
+
+// =================================================================================================
+// runtime
+// =================================================================================================
+extern "C" int ompimg_init(int device) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (g.ready && g.device == device) return OMPIMG_OK;
+    if (g.ready) return fail(OMPIMG_ERR_ARG, "already bound to device %d", g.device);
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(OMPIMG_ERR_CUDA, "no usable CUDA device (%s); libompimg_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count=0");
+    NEED(device >= 0 && device < n, "device index");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(OMPIMG_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    g.sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < OMPIMG_NUM_STREAMS; ++i) {
+        CK(cudaStreamCreateWithFlags(&g.streams[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&g.edge_events[i], cudaEventDisableTiming));
+    }
+    const char *m = getenv("OMPIMG_LUMA");
+    if (m) g.luma_mode = (!strcmp(m, "fma") || !strcmp(m, "1")) ? OMPIMG_LUMA_FMA : OMPIMG_LUMA_STRICT;
+    g.device = device;
+    g.ready = true;
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_device(void) { return g.ready ? g.device : -1; }
+extern "C" int ompimg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" int ompimg_sm_count(void) { return g.ready ? g.sm_count : 0; }
+extern "C" const char *ompimg_last_error(void) { return g_err; }
+extern "C" const char *ompimg_version(void) { return "ompimg_b200 0.1 (sm_100a)"; }
+extern "C" int ompimg_set_luma_mode(int mode) {
+    NEED(mode == OMPIMG_LUMA_STRICT || mode == OMPIMG_LUMA_FMA, "luma mode");
+    g.luma_mode = mode;
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_get_luma_mode(void) { return g.luma_mode; }
+extern "C" long long ompimg_launch_count(void) { return g_launch_count.load(); }
+extern "C" int ompimg_shutdown(void) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!g.ready) return OMPIMG_OK;
+    cudaSetDevice(g.device);
+    cudaDeviceSynchronize();
+    for (auto &b : g.scratch) { if (b.p) cudaFree(b.p); b = DevBuf(); }
+    for (auto &s : g.slots) for (auto &b : s) { if (b.p) cudaFree(b.p); b = DevBuf(); }
+    for (auto &t : g.timers) { if (t.a) cudaEventDestroy(t.a); if (t.b) cudaEventDestroy(t.b); }
+    g.timers.clear();
+    for (int i = 0; i < OMPIMG_NUM_STREAMS; ++i) { cudaStreamDestroy(g.streams[i]); cudaEventDestroy(g.edge_events[i]); }
+    g.ready = false;
+    g.device = -1;
+    return OMPIMG_OK;
+}
+
+extern "C" void *ompimg_dev_alloc(size_t bytes) {
+    if (ensure_init() != OMPIMG_OK) return nullptr;
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) { fail(OMPIMG_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+extern "C" int ompimg_dev_free(void *p) { INIT(); CK(cudaFree(p)); return OMPIMG_OK; }
+extern "C" void *ompimg_host_alloc(size_t bytes) {
+    if (ensure_init() != OMPIMG_OK) return nullptr;
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) { fail(OMPIMG_ERR_NOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+extern "C" int ompimg_host_free(void *p) { INIT(); CK(cudaFreeHost(p)); return OMPIMG_OK; }
+extern "C" int ompimg_host_register(void *p, size_t bytes) { INIT(); CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable)); return OMPIMG_OK; }
+extern "C" int ompimg_host_unregister(void *p) { INIT(); CK(cudaHostUnregister(p)); return OMPIMG_OK; }
+extern "C" int ompimg_memset_dev(void *dst, int value, size_t bytes, int stream) {
+    INIT(); STREAM(stream, st);
+    CK(cudaMemsetAsync(dst, value, bytes, st));
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_copy_h2d(void *dst, const void *src, size_t bytes, int stream) {
+    INIT(); STREAM(stream, st);
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_copy_d2h(void *dst, const void *src, size_t bytes, int stream) {
+    INIT(); STREAM(stream, st);
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_copy_d2d(void *dst, const void *src, size_t bytes, int stream) {
+    INIT(); STREAM(stream, st);
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_copy2d_h2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t wb, size_t rows, int stream) {
+    INIT(); STREAM(stream, st);
+    CK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, wb, rows, cudaMemcpyHostToDevice, st));
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_copy2d_d2h(void *dst, size_t dpitch, const void *src, size_t spitch, size_t wb, size_t rows, int stream) {
+    INIT(); STREAM(stream, st);
+    CK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, wb, rows, cudaMemcpyDeviceToHost, st));
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_stream_sync(int stream) {
+    INIT();
+    if (stream < 0) { for (int i = 0; i < OMPIMG_NUM_STREAMS; ++i) CK(cudaStreamSynchronize(g.streams[i])); return OMPIMG_OK; }
+    STREAM(stream, st);
+    CK(cudaStreamSynchronize(st));
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_stream_wait_stream(int waiter, int signaller) {
+    INIT(); STREAM(waiter, sw); STREAM(signaller, ss);
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    CK(cudaEventRecord(g.edge_events[signaller], ss));
+    CK(cudaStreamWaitEvent(sw, g.edge_events[signaller], 0));
+    return OMPIMG_OK;
+}
+
+extern "C" int ompimg_timer_create(void) {
+    INIT();
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    Timer t;
+    CK(cudaEventCreate(&t.a));
+    CK(cudaEventCreate(&t.b));
+    t.used = true;
+    for (size_t i = 0; i < g.timers.size(); ++i)
+        if (!g.timers[i].used) { g.timers[i] = t; return (int)i; }
+    g.timers.push_back(t);
+    return (int)g.timers.size() - 1;
+}
+static int timer_of(int id, Timer **t) {
+    if (id < 0 || id >= (int)g.timers.size() || !g.timers[id].used) return fail(OMPIMG_ERR_ARG, "bad timer id %d", id);
+    *t = &g.timers[id];
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_timer_start(int id, int stream) {
+    INIT(); STREAM(stream, st);
+    Timer *t; int rc = timer_of(id, &t); if (rc) return rc;
+    CK(cudaEventRecord(t->a, st));
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_timer_stop(int id, int stream) {
+    INIT(); STREAM(stream, st);
+    Timer *t; int rc = timer_of(id, &t); if (rc) return rc;
+    CK(cudaEventRecord(t->b, st));
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_timer_elapsed_ms(int id, float *ms) {
+    INIT();
+    Timer *t; int rc = timer_of(id, &t); if (rc) return rc;
+    CK(cudaEventSynchronize(t->b));
+    CK(cudaEventElapsedTime(ms, t->a, t->b));
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_timer_destroy(int id) {
+    INIT();
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    Timer *t; int rc = timer_of(id, &t); if (rc) return rc;
+    cudaEventDestroy(t->a); cudaEventDestroy(t->b);
+    *t = Timer();
+    return OMPIMG_OK;
+}
+
+// =================================================================================================
+// device-resident entry points
+// =================================================================================================
+extern "C" int ompimg_gray_inplace_dev(uint8_t *img, size_t pitch, int w, int h, int ch, int nframes, size_t fstride, int stream) {
+    INIT(); STREAM(stream, st);
+    NEED(img && w > 0 && h > 0 && nframes > 0, "image");
+    NEED(ch == 3 || ch == 4, "channels must be 3 or 4 (1 and 2 are undefined behaviour in the reference)");
+    NEED(pitch >= (size_t)w * ch, "pitch");
+    CK(launch_gray_inplace(img, pitch, w, h, ch, nframes, fstride, g.luma_mode, g.sm_count, st));
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_rgb_to_luma_dev(const uint8_t *rgb, size_t rgb_pitch, int ch, uint8_t *luma, size_t luma_pitch, int w, int h,
+                                      int nframes, size_t rgb_stride, size_t luma_stride, int stream) {
+    INIT(); STREAM(stream, st);
+    NEED(rgb && luma && w > 0 && h > 0 && nframes > 0, "image");
+    NEED(ch == 3 || ch == 4, "channels must be 3 or 4");
+    NEED(rgb_pitch >= (size_t)w * ch && luma_pitch >= (size_t)w, "pitch");
+    CK(launch_rgb_to_luma(rgb, rgb_pitch, ch, luma, luma_pitch, w, h, nframes, rgb_stride, luma_stride, g.luma_mode, g.sm_count, st));
+    return OMPIMG_OK;
+}
+static int sobel_common(const uint8_t *src, size_t sp, int ch, uint8_t *dst, size_t dp, int w, int h, int nframes, size_t ss, size_t ds,
+                        const uint8_t *above, const uint8_t *below, cudaStream_t st) {
+    StencilArgs a{};
+    a.src = src; a.dst = dst; a.src_pitch = sp; a.dst_pitch = dp; a.src_stride = ss; a.dst_stride = ds;
+    a.width = w; a.height = h; a.channels = ch; a.nframes = nframes; a.fma_mode = g.luma_mode;
+    a.halo_above = above; a.halo_below = below;
+    CK(launch_sobel(a, g.sm_count, st));
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_sobel_dev(const uint8_t *src, size_t sp, uint8_t *dst, size_t dp, int w, int h, int nframes, size_t ss, size_t ds, int stream) {
+    INIT(); STREAM(stream, st);
+    NEED(src && dst && w > 0 && h > 0 && nframes > 0, "image");
+    NEED(sp >= (size_t)w && dp >= (size_t)w, "pitch");
+    return sobel_common(src, sp, 1, dst, dp, w, h, nframes, ss, ds, nullptr, nullptr, st);
+}
+extern "C" int ompimg_rgb_to_edge_dev(const uint8_t *rgb, size_t rp, int ch, uint8_t *edge, size_t ep, int w, int h, int nframes,
+                                      size_t rs, size_t es, int stream) {
+    INIT(); STREAM(stream, st);
+    NEED(rgb && edge && w > 0 && h > 0 && nframes > 0, "image");
+    NEED(ch == 3 || ch == 4, "channels must be 3 or 4");
+    NEED(rp >= (size_t)w * ch && ep >= (size_t)w, "pitch");
+    return sobel_common(rgb, rp, ch, edge, ep, w, h, nframes, rs, es, nullptr, nullptr, st);
+}
+extern "C" int ompimg_rgb_to_edge_band_dev(const uint8_t *rgb, size_t rp, int ch, uint8_t *edge, size_t ep, int w, int band_rows,
+                                           const uint8_t *row_above, const uint8_t *row_below, int stream) {
+    INIT(); STREAM(stream, st);
+    NEED(rgb && edge && w > 0 && band_rows > 0, "band");
+    NEED(ch == 1 || ch == 3 || ch == 4, "channels must be 1, 3 or 4");
+    return sobel_common(rgb, rp, ch, edge, ep, w, band_rows, 1, 0, 0, row_above, row_below, st);
+}
+extern "C" int ompimg_replicate_dev(const uint8_t *plane, size_t pp, uint8_t *img, size_t ip, int ch, int w, int h, int nframes,
+                                    size_t ps, size_t is, int stream) {
+    INIT(); STREAM(stream, st);
+    NEED(plane && img && w > 0 && h > 0 && nframes > 0, "image");
+    NEED(ch == 3 || ch == 4, "channels must be 3 or 4");
+    CK(launch_replicate(plane, pp, img, ip, ch, w, h, nframes, ps, is, g.sm_count, st));
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_gray_sobel_pass_dev(uint8_t *img, size_t ip, int ch, uint8_t *edge, size_t ep, int w, int h, int nframes,
+                                          size_t is, size_t es, int stream) {
+    INIT(); STREAM(stream, st);
+    NEED(img && edge && w > 0 && h > 0 && nframes > 0, "image");
+    NEED(ch == 3 || ch == 4, "channels must be 3 or 4");
+    int rc = sobel_common(img, ip, ch, edge, ep, w, h, nframes, is, es, nullptr, nullptr, st);
+    if (rc) return rc;
+    CK(launch_replicate(edge, ep, img, ip, ch, w, h, nframes, es, is, g.sm_count, st));
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_conv_i32_dev(const uint8_t *in, size_t in_pitch, int rows, int cols, int K, const int32_t *taps, int32_t norm,
+                                   int32_t *out, size_t out_pitch, int stream) {
+    INIT(); STREAM(stream, st);
+    NEED(in && out && taps && rows > 0 && cols > 0, "image");
+    NEED(K >= 1 && K <= 15 && norm != 0, "K in 1..15, norm != 0");
+    CK(launch_conv(in, in_pitch, rows, cols, K, taps, norm, out, out_pitch, 0, g.sm_count, st));
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_conv_u8_dev(const uint8_t *in, size_t in_pitch, int rows, int cols, int K, const int32_t *taps, int32_t norm,
+                                  uint8_t *out, size_t out_pitch, int stream) {
+    INIT(); STREAM(stream, st);
+    NEED(in && out && taps && rows > 0 && cols > 0, "image");
+    NEED(K >= 1 && K <= 15 && norm != 0, "K in 1..15, norm != 0");
+    CK(launch_conv(in, in_pitch, rows, cols, K, taps, norm, out, out_pitch, 1, g.sm_count, st));
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_channel_sums_dev(const uint8_t *rgb, size_t pitch, int rows, int cols, unsigned long long *sums3, int stream) {
+    INIT(); STREAM(stream, st);
+    NEED(rgb && sums3 && rows > 0 && cols > 0, "image");
+    CK(launch_channel_sums(rgb, pitch, rows, cols, sums3, g.sm_count, st));
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_gray_avg3_dev(const uint8_t *rgb, size_t ip, uint8_t *out, size_t op, int rows, int cols, int *min_max, int stream) {
+    INIT(); STREAM(stream, st);
+    NEED(rgb && out && min_max && rows > 0 && cols > 0, "image");
+    CK(launch_gray_avg3(rgb, ip, out, op, rows, cols, min_max, g.sm_count, st));
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_synth_fill_dev(uint8_t *dst, unsigned long long nbytes, unsigned int seed, unsigned long long off, int stream) {
+    INIT(); STREAM(stream, st);
+    NEED(dst || nbytes == 0, "dst");
+    if (nbytes == 0) return OMPIMG_OK;
+    CK(launch_synth(dst, nbytes, seed, off, g.sm_count, st));
+    return OMPIMG_OK;
+}
+
+// =================================================================================================
+// self tests
+// =================================================================================================
+extern "C" int ompimg_selftest_luma_lut(uint8_t *lut_host, int mode) {
+    INIT();
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    NEED(lut_host, "lut");
+    RESERVE(g.scratch[0], (size_t)1 << 24);
+    CK(launch_luma_lut((uint8_t *)g.scratch[0].p, mode, g.streams[0]));
+    CK(cudaMemcpyAsync(lut_host, g.scratch[0].p, (size_t)1 << 24, cudaMemcpyDeviceToHost, g.streams[0]));
+    CK(cudaStreamSynchronize(g.streams[0]));
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_selftest_isqrt(uint8_t *out_host, unsigned int count) {
+    INIT();
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    NEED(out_host && count > 0, "out");
+    RESERVE(g.scratch[0], count);
+    CK(launch_isqrt_selftest((uint8_t *)g.scratch[0].p, count, g.streams[0]));
+    CK(cudaMemcpyAsync(out_host, g.scratch[0].p, count, cudaMemcpyDeviceToHost, g.streams[0]));
+    CK(cudaStreamSynchronize(g.streams[0]));
+    return OMPIMG_OK;
+}
+
+// =================================================================================================
+// host-buffer pipelines
+// =================================================================================================
+// a1 through host memory: the image is cut into chunks of whole 16-pixel groups; chunk i goes
+// H2D -> kernel -> D2H on stream i % NS, so the upload of one chunk overlaps the kernel and the
+// download of the previous ones (PCIe is full duplex).
+extern "C" int ompimg_gray_inplace_host(uint8_t *data, int w, int h, int ch) {
+    INIT();
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    NEED(data && w > 0 && h > 0, "image");
+    NEED(ch == 3 || ch == 4, "channels must be 3 or 4 (1 and 2 are undefined behaviour in the reference)");
+    const size_t npx = (size_t)w * h, bytes = npx * ch;
+    ScopedPin pin(data, bytes);
+    RESERVE(g.scratch[0], bytes + 256);
+    uint8_t *d = (uint8_t *)g.scratch[0].p;
+    const size_t min_chunk_px = 256 * 1024;           // >= 0.75 MB per copy
+    size_t nchunks = npx / min_chunk_px;
+    if (nchunks < 1) nchunks = 1;
+    if (nchunks > 2 * OMPIMG_NUM_STREAMS) nchunks = 2 * OMPIMG_NUM_STREAMS;
+    const size_t chunk_px = round_up((npx + nchunks - 1) / nchunks, 16);
+    int i = 0;
+    for (size_t p0 = 0; p0 < npx; p0 += chunk_px, ++i) {
+        const size_t n = npx - p0 < chunk_px ? npx - p0 : chunk_px;
+        cudaStream_t st = g.streams[i % OMPIMG_NUM_STREAMS];
+        CK(cudaMemcpyAsync(d + p0 * ch, data + p0 * ch, n * ch, cudaMemcpyHostToDevice, st));
+        CK(launch_gray_inplace(d + p0 * ch, n * ch, (int)n, 1, ch, 1, 0, g.luma_mode, g.sm_count, st));
+        CK(cudaMemcpyAsync(data + p0 * ch, d + p0 * ch, n * ch, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < OMPIMG_NUM_STREAMS && s < i; ++s) CK(cudaStreamSynchronize(g.streams[s]));
+    return OMPIMG_OK;
+}
+
+// a2 through host memory.  The device copies are pitched (pitch % 128 == 0) so that any width takes
+// the bulk-copy kernel; only the interior of dst travels back, which is what keeps the caller's
+// border bytes untouched.  Row bands (with their halo rows) go through the streams independently.
+extern "C" int ompimg_sobel_host(const uint8_t *src, uint8_t *dst, int w, int h) {
+    INIT();
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    NEED(src && dst && w > 0 && h > 0, "image");
+    if (w < 3 || h < 3) return OMPIMG_OK;              // sobel.c:11-12: no interior, nothing written
+    const size_t pitch = round_up((size_t)w, 128);
+    ScopedPin pin_s(src, (size_t)w * h), pin_d(dst, (size_t)w * h);
+    RESERVE(g.scratch[0], pitch * h + 256);
+    RESERVE(g.scratch[1], pitch * h + 256);
+    uint8_t *ds = (uint8_t *)g.scratch[0].p, *dd = (uint8_t *)g.scratch[1].p;
+    const int interior = h - 2;
+    int nb = (int)(((size_t)w * h) / (1 << 20));
+    if (nb < 1) nb = 1;
+    if (nb > OMPIMG_NUM_STREAMS) nb = OMPIMG_NUM_STREAMS;
+    const int rows_per = (interior + nb - 1) / nb;
+    int i = 0;
+    for (int y0 = 1; y0 < h - 1; y0 += rows_per, ++i) {
+        const int y1 = y0 + rows_per < h - 1 ? y0 + rows_per : h - 1;   // output rows [y0, y1)
+        cudaStream_t st = g.streams[i % OMPIMG_NUM_STREAMS];
+        const int r0 = y0 - 1, nr = y1 - y0 + 2;                          // source rows incl. halo
+        CK(cudaMemcpy2DAsync(ds + (size_t)r0 * pitch, pitch, src + (size_t)r0 * w, w, w, nr, cudaMemcpyHostToDevice, st));
+        int rc = sobel_common(ds + (size_t)r0 * pitch, pitch, 1, dd + (size_t)r0 * pitch, pitch, w, nr, 1, 0, 0, nullptr, nullptr, st);
+        if (rc) return rc;
+        CK(cudaMemcpy2DAsync(dst + (size_t)y0 * w + 1, w, dd + (size_t)y0 * pitch + 1, pitch, w - 2, y1 - y0, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < OMPIMG_NUM_STREAMS && s < i; ++s) CK(cudaStreamSynchronize(g.streams[s]));
+    return OMPIMG_OK;
+}
+
+// a5 through host memory: one iteration of main_with_sobel.c:51-74 on the caller's image.
+extern "C" int ompimg_gray_sobel_pass_host(uint8_t *img, int w, int h, int ch, uint8_t *edge) {
+    INIT();
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    NEED(img && w > 0 && h > 0, "image");
+    NEED(ch == 3 || ch == 4, "channels must be 3 or 4");
+    const size_t row = (size_t)w * ch, ipitch = round_up(row, 128), epitch = round_up((size_t)w, 128);
+    ScopedPin pin_i(img, row * h);
+    RESERVE(g.scratch[0], ipitch * h + 256);
+    RESERVE(g.scratch[1], epitch * h + 256);
+    uint8_t *di = (uint8_t *)g.scratch[0].p, *de = (uint8_t *)g.scratch[1].p;
+    cudaStream_t st = g.streams[0];
+    CK(cudaMemcpy2DAsync(di, ipitch, img, row, row, h, cudaMemcpyHostToDevice, st));
+    if (edge) CK(cudaMemcpy2DAsync(de, epitch, edge, w, w, h, cudaMemcpyHostToDevice, st));   // the scratch plane's border survives the pass
+    else CK(cudaMemsetAsync(de, 0, epitch * h, st));
+    int rc = sobel_common(di, ipitch, ch, de, epitch, w, h, 1, 0, 0, nullptr, nullptr, st);
+    if (rc) return rc;
+    CK(launch_replicate(de, epitch, di, ipitch, ch, w, h, 1, 0, 0, g.sm_count, st));
+    CK(cudaMemcpy2DAsync(img, row, di, ipitch, row, h, cudaMemcpyDeviceToHost, st));
+    if (edge) CK(cudaMemcpy2DAsync(edge, w, de, epitch, w, h, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return OMPIMG_OK;
+}
+
+// batch of frames, host -> host.  Frame f uses slot/stream f % NS: upload, fused kernel, download.
+extern "C" int ompimg_rgb_to_edge_batch_host(const uint8_t *rgb, size_t rgb_stride, int ch, uint8_t *edge, size_t edge_stride,
+                                             int w, int h, int nframes) {
+    INIT();
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    NEED(rgb && edge && w > 0 && h > 0 && nframes > 0, "batch");
+    NEED(ch == 3 || ch == 4, "channels must be 3 or 4");
+    const size_t row = (size_t)w * ch, ipitch = round_up(row, 128), epitch = round_up((size_t)w, 128);
+    NEED(rgb_stride >= row * h && edge_stride >= (size_t)w * h, "strides");
+    const int ns = nframes < OMPIMG_NUM_STREAMS ? nframes : OMPIMG_NUM_STREAMS;
+    for (int s = 0; s < ns; ++s) {
+        const bool fresh = g.slots[s][1].cap < epitch * h + 256;
+        RESERVE(g.slots[s][0], ipitch * h + 256);
+        RESERVE(g.slots[s][1], epitch * h + 256);
+        (void)fresh;
+        // the kernel never writes border bytes, so one memset per call gives every frame a zero border
+        CK(cudaMemsetAsync(g.slots[s][1].p, 0, epitch * h, g.streams[s]));
+    }
+    for (int f = 0; f < nframes; ++f) {
+        const int s = f % ns;
+        cudaStream_t st = g.streams[s];
+        uint8_t *di = (uint8_t *)g.slots[s][0].p, *de = (uint8_t *)g.slots[s][1].p;
+        if (ipitch == row) CK(cudaMemcpyAsync(di, rgb + (size_t)f * rgb_stride, row * h, cudaMemcpyHostToDevice, st));
+        else CK(cudaMemcpy2DAsync(di, ipitch, rgb + (size_t)f * rgb_stride, row, row, h, cudaMemcpyHostToDevice, st));
+        int rc = sobel_common(di, ipitch, ch, de, epitch, w, h, 1, 0, 0, nullptr, nullptr, st);
+        if (rc) return rc;
+        if (epitch == (size_t)w) CK(cudaMemcpyAsync(edge + (size_t)f * edge_stride, de, (size_t)w * h, cudaMemcpyDeviceToHost, st));
+        else CK(cudaMemcpy2DAsync(edge + (size_t)f * edge_stride, w, de, epitch, w, h, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < ns; ++s) CK(cudaStreamSynchronize(g.streams[s]));
+    return OMPIMG_OK;
+}
+
+extern "C" int ompimg_conv_i32_host(const uint8_t *in_padded, int rows, int cols, int K, const int32_t *taps, int32_t norm, int32_t *out) {
+    INIT();
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    NEED(in_padded && out && taps && rows > 0 && cols > 0, "image");
+    NEED(K >= 1 && K <= 15 && norm != 0, "K in 1..15, norm != 0");
+    const size_t in_row = (size_t)(cols + K - 1) * 3, in_bytes = in_row * (rows + K - 1);
+    const size_t out_row = (size_t)cols * 3 * sizeof(int32_t), out_bytes = out_row * rows;
+    RESERVE(g.scratch[0], in_bytes + 256);
+    RESERVE(g.scratch[1], out_bytes + 256);
+    cudaStream_t st = g.streams[0];
+    CK(cudaMemcpyAsync(g.scratch[0].p, in_padded, in_bytes, cudaMemcpyHostToDevice, st));
+    CK(launch_conv((const uint8_t *)g.scratch[0].p, in_row, rows, cols, K, taps, norm, g.scratch[1].p, out_row, 0, g.sm_count, st));
+    CK(cudaMemcpyAsync(out, g.scratch[1].p, out_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return OMPIMG_OK;
+}
+
+extern "C" int ompimg_avg_pixel_host(const uint8_t *rgb, int rows, int cols, long long *avgs) {
+    INIT();
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    NEED(rgb && avgs && rows > 0 && cols > 0, "image");
+    const size_t bytes = (size_t)rows * cols * 3;
+    RESERVE(g.scratch[0], bytes + 256);
+    RESERVE(g.scratch[2], 64);
+    cudaStream_t st = g.streams[0];
+    unsigned long long sums[3] = {0, 0, 0};
+    CK(cudaMemsetAsync(g.scratch[2].p, 0, 24, st));
+    CK(cudaMemcpyAsync(g.scratch[0].p, rgb, bytes, cudaMemcpyHostToDevice, st));
+    CK(launch_channel_sums((const uint8_t *)g.scratch[0].p, (size_t)cols * 3, rows, cols, (unsigned long long *)g.scratch[2].p, g.sm_count, st));
+    CK(cudaMemcpyAsync(sums, g.scratch[2].p, 24, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // old/parallel_avg_pixel.c: every channel is summed three times (:19-23), added onto avgs (:28-30)
+    // and divided by rows*cols*3 (:8,:40)
+    const long long count = (long long)rows * cols * 3;
+    for (int c = 0; c < 3; ++c) avgs[c] = (avgs[c] + 3 * (long long)sums[c]) / count;
+    return OMPIMG_OK;
+}
+
+extern "C" int ompimg_gray_avg3_host(const uint8_t *rgb, uint8_t *out, int rows, int cols, int *min_max) {
+    INIT();
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    NEED(rgb && out && min_max && rows > 0 && cols > 0, "image");
+    const size_t bytes = (size_t)rows * cols * 3;
+    RESERVE(g.scratch[0], bytes + 256);
+    RESERVE(g.scratch[1], bytes + 256);
+    RESERVE(g.scratch[2], 64);
+    cudaStream_t st = g.streams[0];
+    const int init[2] = {256, -1};      // old/parallel_to_grayscale.c:9-10
+    CK(cudaMemcpyAsync(g.scratch[2].p, init, sizeof init, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(g.scratch[0].p, rgb, bytes, cudaMemcpyHostToDevice, st));
+    CK(launch_gray_avg3((const uint8_t *)g.scratch[0].p, (size_t)cols * 3, (uint8_t *)g.scratch[1].p, (size_t)cols * 3, rows, cols,
+                        (int *)g.scratch[2].p, g.sm_count, st));
+    CK(cudaMemcpyAsync(out, g.scratch[1].p, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(min_max, g.scratch[2].p, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return OMPIMG_OK;
+}
+
+// =================================================================================================
+// the frozen reference prototypes
+// =================================================================================================
+static void die(const char *fn) {
+    fprintf(stderr, "libompimg_b200: %s failed: %s\n", fn, g_err);
+    abort();
+}
+// monolithic/include/parallel_to_grayscale.h:4
+extern "C" void convert_to_grayscale(unsigned char *data, int width, int height, int channels) {
+    if (width <= 0 || height <= 0) return;              // the reference's loop body never runs
+    if (ompimg_gray_inplace_host(data, width, height, channels) != OMPIMG_OK) die("convert_to_grayscale");
+}
+// monolithic/include/sobel.h:3-5
+extern "C" void sobel_edge(const unsigned char *src, unsigned char *dst, int width, int height) {
+    if (width < 3 || height < 3) return;                // no interior pixels: the reference writes nothing
+    if (ompimg_sobel_host(src, dst, width, height) != OMPIMG_OK) die("sobel_edge");
+}

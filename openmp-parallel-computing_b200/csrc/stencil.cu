@@ -1,0 +1,302 @@
+// stencil.cu -- 3x3 Sobel (a2: monolithic/src/sobel.c:6-25) and the fused RGB -> luma -> Sobel path
+// (a3..a5: monolithic/src/main_with_sobel.c:51-74), as one row-streaming kernel.
+//
+// Decomposition: a CTA owns a band of rows of one frame and a column strip of up to NW*512 pixels.
+// A producer warp streams the band's source rows into a ring of shared-memory stages with 1-D bulk
+// asynchronous copies (TMA engine, completion on an mbarrier).  NW consumer warps each own 512
+// columns (16 pixels per lane) and walk down the rows keeping the two previous rows' horizontal
+// partial results in registers (f16x2 pairs), so every source byte is read from HBM once, touched
+// in shared memory once, and the luma plane of the fused path never exists in memory.  The only
+// neighbour exchange is one luma value per warp edge per row (shuffles inside a warp, 8 bytes of
+// shared memory between warps).  Filter taps are immediates folded into the f16x2 arithmetic.
+//
+// Row-band mode (ompimg_bands_*): the rows just above/below the band live on a peer GPU; the
+// producer warp fetches them with ordinary global loads through the NVLink peer mapping.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ompimg {
+
+constexpr int ST_MAX_NW = 8;
+
+struct StencilParams {
+    const uint8_t *src;
+    uint8_t *dst;
+    size_t src_pitch, dst_pitch, src_stride, dst_stride;
+    const uint8_t *halo_above, *halo_below;
+    int width, height;
+    int nbands, rows_per_band;
+    int nw;             // consumer warps
+    int stages;
+    uint32_t stage_bytes;
+    uint32_t row_bytes16;   // round16(width*bpp)
+};
+
+template <int CH>
+__device__ __forceinline__ void load_group_words(uint32_t addr, uint32_t (&w)[4 * CH]) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        const uint4 v = lds128(addr + 16 * i);
+        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+    }
+}
+
+template <int CH, int FMA_MODE>
+__global__ void __launch_bounds__((ST_MAX_NW + 1) * 32) sobel_rows_kernel(const StencilParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int BPP = CH;                      // bytes per source pixel
+    const int NW = p.nw, S = p.stages;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t full0 = smem0 + S * p.stage_bytes;     // S full barriers, S empty barriers, edge exchange
+    const uint32_t empty0 = full0 + 8 * S;
+    const uint32_t edge0 = empty0 + 8 * S;                // [2][NW][2] words
+
+    const int frame = blockIdx.x / p.nbands, band = blockIdx.x - frame * p.nbands;
+    const int SW = NW * 512;
+    const int xs = blockIdx.y * SW;
+    const uint8_t *src = p.src + (size_t)frame * p.src_stride;
+    uint8_t *dst = p.dst + (size_t)frame * p.dst_stride;
+
+    const int ya = band * p.rows_per_band, yb = min(p.height, ya + p.rows_per_band);
+    const int rin0 = max(ya - 1, p.halo_above ? -1 : 0);
+    const int rin1 = min(yb, p.halo_below ? p.height : p.height - 1);
+    const int nin = rin1 - rin0 + 1;              // source rows this CTA consumes; outputs rows rin0+1 .. rin1-1
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NW); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (nin < 3) return;
+
+    if (warp == NW) {
+        // ------------------------------------------------------------------ producer warp
+        const uint32_t lo = xs == 0 ? 0u : (uint32_t)xs * BPP - 16u;
+        const uint32_t hi = min(p.row_bytes16, (uint32_t)(xs + SW) * BPP + 16u);
+        const uint32_t bytes = hi - lo;
+        const uint32_t dst_off = xs == 0 ? 16u : 0u;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < nin; ++i) {
+            const int r = rin0 + i;
+            if (i >= S) mbar_wait(empty0 + 8 * s, ph ^ 1);
+            const uint32_t d = smem0 + s * p.stage_bytes + dst_off;
+            if (r >= 0 && r < p.height) {
+                if (lane == 0) {
+                    mbar_expect_tx(full0 + 8 * s, bytes);
+                    bulk_g2s(d, src + (size_t)r * p.src_pitch + lo, bytes, full0 + 8 * s);
+                }
+            } else {
+                // halo row owned by a neighbouring band (peer device memory over NVLink)
+                const uint8_t *row = (r < 0 ? p.halo_above : p.halo_below) + lo;
+                for (uint32_t j = lane * 16; j < bytes; j += 32 * 16) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(row + j);
+                    sts128(d + j, v);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full0 + 8 * s);
+            }
+            if (++s == S) { s = 0; ph ^= 1; }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumer warps
+    const int c = warp * 32 + lane;               // 16-pixel group index inside the strip
+    const int x0 = xs + 16 * c;
+    const bool active = x0 < p.width;
+    const bool full_store = x0 >= 16 && x0 + 16 <= p.width - 1;
+    const int pfirst = x0 == 0 ? 1 : 0, plast = min(16, p.width - 1 - x0);
+    const uint32_t goff = 16u + (uint32_t)c * (16u * BPP);
+    float half = 0.5f;
+    asm volatile("" : "+f"(half));                // keep 0.5 in a register (FHFMA takes no immediate addend)
+
+    SobelRowState st[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) st[k].sab = st[k].dhb = st[k].sha = st[k].shb = 0u;
+
+    int s = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < nin; ++i) {
+        const uint32_t stage = smem0 + s * p.stage_bytes;
+        mbar_wait(full0 + 8 * s, ph);
+        uint32_t P[8], Q[9];
+        if (CH == 1) {
+            const uint32_t C64 = 0x64646464u;
+            const uint4 v = lds128(stage + goff);
+            const uint32_t lw = lds32(stage + goff - 4), rw = lds32(stage + goff + 16);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * s);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                P[2 * j] = prmt(w[j], C64, 0x4140);
+                P[2 * j + 1] = prmt(w[j], C64, 0x4342);
+                Q[2 * j + 1] = prmt(w[j], C64, 0x4241);
+            }
+            Q[0] = prmt(prmt(lw, C64, 0x4342), P[0], 0x5432);
+#pragma unroll
+            for (int j = 1; j < 4; ++j) Q[2 * j] = prmt(P[2 * j - 1], P[2 * j], 0x5432);
+            Q[8] = prmt(P[7], prmt(rw, C64, 0x4140), 0x5432);
+        } else {
+            uint32_t w[4 * CH];
+            load_group_words<CH>(stage + goff, w);
+            // strip-edge halo pixels (only when the image is wider than one strip)
+            uint32_t eL = 0, eR = 0;
+            const bool needL = warp == 0 && lane == 0 && xs > 0;
+            const bool needR = warp == NW - 1 && lane == 31 && xs + SW < p.width;
+            if (needL) eL = lds32(stage + 16 - 4) >> (8 * (4 - BPP));                    // bytes of pixel xs-1 in the low lanes
+            if (needR) eR = lds32(stage + 16 + (uint32_t)SW * BPP);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * s);
+            uint32_t f[16];
+            const float MAGIC = 14942208.0f;      // 2^23 + 0x640000: result bits 0x4B6400ll
+            if (CH == 3) luma16_rgb<FMA_MODE>(reinterpret_cast<const uint32_t(&)[12]>(w), f, MAGIC);
+            else luma16_rgba<FMA_MODE>(reinterpret_cast<const uint32_t(&)[16]>(w), f, MAGIC);
+            // one luma per warp edge per row goes through shared memory, double-buffered by row parity
+            const uint32_t ex = edge0 + (uint32_t)(i & 1) * (NW * 8);
+            if (lane == 0) sts32(ex + warp * 8, f[0]);
+            if (lane == 31) sts32(ex + warp * 8 + 4, f[15]);
+            named_bar_sync(1, NW * 32);
+            uint32_t fL = __shfl_up_sync(0xffffffffu, f[15], 1);
+            uint32_t fR = __shfl_down_sync(0xffffffffu, f[0], 1);
+            if (lane == 0 && warp > 0) fL = lds32(ex + (warp - 1) * 8 + 4);
+            if (lane == 31 && warp < NW - 1) fR = lds32(ex + (warp + 1) * 8);
+            if (needL) fL = 0x4B640000u | luma1<FMA_MODE>(eL & 255u, (eL >> 8) & 255u, (eL >> 16) & 255u);
+            if (needR) fR = 0x4B640000u | luma1<FMA_MODE>(eR & 255u, (eR >> 8) & 255u, (eR >> 16) & 255u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) P[k] = prmt(f[2 * k], f[2 * k + 1], 0x6420);
+            Q[0] = prmt(fL, f[0], 0x6420);
+#pragma unroll
+            for (int k = 1; k < 8; ++k) Q[k] = prmt(f[2 * k - 1], f[2 * k], 0x6420);
+            Q[8] = prmt(f[15], fR, 0x6420);
+        }
+        uint32_t gx[8], gy[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sobel_pair(P[k], Q[k], Q[k + 1], st[k], gx[k], gy[k]);
+        if (i >= 2 && active) {
+            const uint4 o = sobel_mag16(gx, gy, half);
+            uint8_t *out = dst + (size_t)(rin0 + i - 1) * p.dst_pitch + x0;
+            if (full_store) *reinterpret_cast<uint4 *>(out) = o;
+            else store_partial16(out, o, pfirst, plast);
+        }
+        if (++s == S) { s = 0; ph ^= 1; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic fallback (any alignment / pitch): one thread per output pixel
+// ---------------------------------------------------------------------------------------------
+template <int CH, int FMA_MODE>
+__device__ __forceinline__ int px_value(const uint8_t *row, int x) {
+    if (CH == 1) return row[x];
+    return (int)luma1<FMA_MODE>(row[x * CH], row[x * CH + 1], row[x * CH + 2]);
+}
+__device__ __forceinline__ uint32_t isqrt_clamp255(uint32_t m) {
+    if (m >= 65025u) return 255u;
+    uint32_t r = (uint32_t)sqrtf((float)m);      // correctly rounded sqrt of an exact float; fix the edges anyway
+    while (r * r > m) --r;
+    while ((r + 1) * (r + 1) <= m) ++r;
+    return r;
+}
+template <int CH, int FMA_MODE>
+__global__ void __launch_bounds__(256) sobel_generic_kernel(const StencilArgs a) {
+    const long long iw = a.width - 2;
+    const int ylo = (a.halo_above ? 0 : 1), yhi = (a.halo_below ? a.height - 1 : a.height - 2);   // inclusive output rows
+    const long long ih = yhi - ylo + 1;
+    if (iw <= 0 || ih <= 0) return;
+    const long long total = (long long)a.nframes * ih * iw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long f = i / (ih * iw), rem = i - f * ih * iw;
+        const int y = ylo + (int)(rem / iw), x = 1 + (int)(rem % iw);
+        const uint8_t *base = a.src + f * a.src_stride;
+        const uint8_t *ra = (y - 1 < 0) ? a.halo_above : base + (size_t)(y - 1) * a.src_pitch;
+        const uint8_t *rb = base + (size_t)y * a.src_pitch;
+        const uint8_t *rc = (y + 1 >= a.height) ? a.halo_below : base + (size_t)(y + 1) * a.src_pitch;
+        const int a0 = px_value<CH, FMA_MODE>(ra, x - 1), a1 = px_value<CH, FMA_MODE>(ra, x), a2 = px_value<CH, FMA_MODE>(ra, x + 1);
+        const int b0 = px_value<CH, FMA_MODE>(rb, x - 1), b2 = px_value<CH, FMA_MODE>(rb, x + 1);
+        const int c0 = px_value<CH, FMA_MODE>(rc, x - 1), c1 = px_value<CH, FMA_MODE>(rc, x), c2 = px_value<CH, FMA_MODE>(rc, x + 1);
+        const int gx = -a0 - 2 * b0 - c0 + a2 + 2 * b2 + c2;
+        const int gy = a0 + 2 * a1 + a2 - c0 - 2 * c1 - c2;
+        a.dst[f * a.dst_stride + (size_t)y * a.dst_pitch + x] = (uint8_t)isqrt_clamp255((uint32_t)(gx * gx + gy * gy));
+    }
+}
+
+template <int CH, int FMA_MODE>
+static cudaError_t launch_sobel_t(const StencilArgs &a, int sm_count, cudaStream_t st) {
+    if (a.width < 3 || a.nframes < 1) return cudaSuccess;
+    const int out_rows = a.height - (a.halo_above ? 0 : 1) - (a.halo_below ? 0 : 1);
+    if (out_rows < 1) return cudaSuccess;
+    const bool fast = (((uintptr_t)a.src | (uintptr_t)a.dst | (uintptr_t)a.halo_above | (uintptr_t)a.halo_below) & 15) == 0 &&
+                      ((a.src_pitch | a.dst_pitch) & 15) == 0 && (a.nframes == 1 || ((a.src_stride | a.dst_stride) & 15) == 0) &&
+                      a.src_pitch >= (((size_t)a.width * CH + 15) & ~(size_t)15);
+    if (!fast) {
+        const long long total = (long long)a.nframes * out_rows * (a.width - 2);
+        const int grid = (int)max(1LL, min((total + 255) / 256, (long long)sm_count * 16));
+        count_launch();
+        sobel_generic_kernel<CH, FMA_MODE><<<grid, 256, 0, st>>>(a);
+        return cudaGetLastError();
+    }
+    StencilParams p{};
+    p.src = a.src; p.dst = a.dst; p.src_pitch = a.src_pitch; p.dst_pitch = a.dst_pitch;
+    p.src_stride = a.src_stride; p.dst_stride = a.dst_stride;
+    p.halo_above = a.halo_above; p.halo_below = a.halo_below;
+    p.width = a.width; p.height = a.height;
+    p.nw = min(ST_MAX_NW, (a.width + 511) / 512);
+    const int nstrips = (a.width + p.nw * 512 - 1) / (p.nw * 512);
+    p.row_bytes16 = (uint32_t)(((size_t)a.width * CH + 15) & ~(size_t)15);
+    p.stage_bytes = (uint32_t)((32 + p.nw * 512 * CH + 127) & ~127);
+    // occupancy target: ~24-32 resident warps per SM
+    const int occ = max(1, min(4, 30 / (p.nw + 1)));
+    const int budget = (227 * 1024) / occ - 1024 - 512;
+    p.stages = max(3, min(12, budget / (int)p.stage_bytes));
+    const int smem = p.stages * (int)p.stage_bytes + 16 * p.stages + 2 * p.nw * 8 + 64;
+    // bands: ~128 rows when there is plenty of work, fewer rows (>=16) when the launch is small
+    const long long want_ctas = (long long)sm_count * occ * 4;
+    int rpb = 128;
+    while (rpb > 16 && (long long)a.nframes * nstrips * ((a.height + rpb - 1) / rpb) < want_ctas) rpb /= 2;
+    if (rpb > a.height) rpb = a.height;
+    p.rows_per_band = rpb;
+    p.nbands = (a.height + rpb - 1) / rpb;
+
+    static unsigned long long attr_mask = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (!(attr_mask >> dev & 1ULL)) {
+        e = cudaFuncSetAttribute(sobel_rows_kernel<CH, FMA_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_mask |= 1ULL << dev;
+    }
+    const long long gx = (long long)a.nframes * p.nbands;
+    if (gx > 0x7fffffffLL || nstrips > 65535) return cudaErrorInvalidValue;
+    count_launch();
+    sobel_rows_kernel<CH, FMA_MODE><<<dim3((unsigned)gx, (unsigned)nstrips), (p.nw + 1) * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sobel(const StencilArgs &a, int sm_count, cudaStream_t st) {
+    switch (a.channels) {
+        case 1: return launch_sobel_t<1, 0>(a, sm_count, st);
+        case 3: return a.fma_mode ? launch_sobel_t<3, 1>(a, sm_count, st) : launch_sobel_t<3, 0>(a, sm_count, st);
+        case 4: return a.fma_mode ? launch_sobel_t<4, 1>(a, sm_count, st) : launch_sobel_t<4, 0>(a, sm_count, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------------------------
+// self tests of the magnitude path
+// ---------------------------------------------------------------------------------------------
+// out[m] = sat_u8(trunc(sqrt.approx(m + 0.5)))  -- must equal min(255, isqrt(m)) for every m
+__global__ void isqrt_selftest_kernel(uint8_t *out, unsigned int count) {
+    for (unsigned int m = blockIdx.x * blockDim.x + threadIdx.x; m < count; m += gridDim.x * blockDim.x)
+        out[m] = (uint8_t)(pack_sat_u8(0.f, sqrt_approx((float)m + 0.5f), 0u) & 255u);
+}
+cudaError_t launch_isqrt_selftest(uint8_t *out_dev, unsigned int count, cudaStream_t st) {
+    count_launch();
+    isqrt_selftest_kernel<<<1024, 256, 0, st>>>(out_dev, count);
+    return cudaGetLastError();
+}
+
+}  // namespace ompimg

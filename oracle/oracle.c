@@ -165,6 +165,24 @@ ORACLE_API void oracle_gray_sobel_pass(unsigned char *img, int w, int h, int cha
     }
 }
 
+/* The driver's two glue loops on their own (main_with_sobel.c:57-59 and :65-73), so that
+ * bench.py --impl reference can time the compiled reference functions (oracle/_ref) around them. */
+ORACLE_API void oracle_extract_plane(const unsigned char *img, long long npixels, int channels, unsigned char *gray)
+{
+    #pragma omp parallel for schedule(static)
+    for (long long i = 0; i < npixels; ++i) gray[i] = img[i * channels];
+}
+
+ORACLE_API void oracle_replicate_plane(const unsigned char *edge, long long npixels, int channels, unsigned char *img)
+{
+    #pragma omp parallel for schedule(static)
+    for (long long i = 0; i < npixels; ++i) {
+        unsigned char e = edge[i];
+        unsigned char *p = img + i * channels;
+        p[0] = e; p[1] = e; p[2] = e;
+    }
+}
+
 /* Fused statement of the same pass without the RGB round trip: RGB(A) in, edge
  * plane out (interior only).  Equal to sobel(luma(rgb)) by construction. */
 ORACLE_API void oracle_rgb_to_edge(const unsigned char *rgb, size_t rgb_pitch, int channels,

@@ -57,11 +57,13 @@ def lib() -> C.CDLL:
         L.oracle_avg_pixel_u8.argtypes = [_u8p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
         L.oracle_gray_avg3_long.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.oracle_gray_avg3_u8.argtypes = [_u8p, C.c_size_t, _u8p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+        L.oracle_extract_plane.argtypes = [_u8p, C.c_longlong, C.c_int, _u8p]
+        L.oracle_replicate_plane.argtypes = [_u8p, C.c_longlong, C.c_int, _u8p]
         L.oracle_synth_fill.argtypes = [_u8p, C.c_ulonglong, C.c_uint, C.c_ulonglong]
         for f in ("oracle_gray_inplace oracle_gray_lut oracle_rgb_to_luma oracle_sobel oracle_sobel_isqrt "
                   "oracle_gray_sobel_pass oracle_rgb_to_edge oracle_convolution_long oracle_convolution_u8 "
                   "oracle_avg_pixel_long oracle_avg_pixel_u8 oracle_gray_avg3_long oracle_gray_avg3_u8 "
-                  "oracle_synth_fill").split():
+                  "oracle_synth_fill oracle_extract_plane oracle_replicate_plane").split():
             getattr(L, f).restype = None
         _lib = L
     return _lib

@@ -1,0 +1,400 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI of
+libompimg_b200.so, against the CPU oracle on the same inputs, against the golden vectors generated
+from the unmodified reference, and -- at BASELINE.json's full sizes -- through size-independent
+properties.  Everything is bit-exact: these are uint8/int32 results."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from common import SYNTH_SHAPES, fixture_raw, png, sha
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def to_dev_pitched(gpu, a2d: np.ndarray, pitch: int, pad_value: int = 0xCD):
+    """rows x row_bytes numpy -> device buffer with the given pitch (padding pre-filled)."""
+    rows, rb = a2d.shape
+    buf = gpu.DeviceBuffer(pitch * rows + 64)
+    buf.fill(pad_value)
+    L = gpu.lib()
+    a2d = np.ascontiguousarray(a2d)
+    assert L.ompimg_copy2d_h2d(buf.ptr, pitch, a2d.ctypes.data, rb, rb, rows, 0) == 0
+    gpu.sync(0)
+    return buf
+
+
+def from_dev_pitched(gpu, buf, rows: int, rb: int, pitch: int) -> np.ndarray:
+    out = np.empty((rows, rb), np.uint8)
+    assert gpu.lib().ompimg_copy2d_d2h(out.ctypes.data, rb, buf.ptr, pitch, rb, rows, 0) == 0
+    gpu.sync(0)
+    return out
+
+
+def ck(gpu, rc):
+    assert rc == 0, gpu.lib().ompimg_last_error().decode()
+
+
+# ------------------------------------------------------------------------------------------------ arithmetic
+@pytest.mark.parametrize("mode,key", [("strict", "strict"), ("fma", "mono")])
+def test_luma_all_2_24_triples(gpu, O, golden, mode, key):
+    lut = gpu.luma_lut(mode)
+    assert sha(lut) == golden["lut_sha256"][key]
+    assert np.array_equal(lut, O.gray_lut(mode == "fma"))
+
+
+def test_isqrt_path_exhaustive(gpu):
+    """sat_u8(trunc(sqrt.approx(m+0.5))) == min(255, isqrt(m)) for every reachable m = gx^2+gy^2 <= 2*1020^2."""
+    n = 2 * 1020 * 1020 + 1
+    got = gpu.isqrt_table(n)
+    m = np.arange(n, dtype=np.int64)
+    r = np.floor(np.sqrt(m.astype(np.float64))).astype(np.int64)
+    r = np.where(r * r > m, r - 1, r)
+    r = np.where((r + 1) * (r + 1) <= m, r + 1, r)
+    assert np.array_equal(got, np.minimum(r, 255).astype(np.uint8))
+
+
+def test_synth_matches_oracle(gpu, O):
+    for n, seed, off in [(1, 1, 0), (17, 2, 3), (4096 + 5, 3, 0), (1 << 20, 0xB2000003, 12345), (999, 7, 1 << 33)]:
+        buf = gpu.DeviceBuffer(n + 64)
+        for dst_off in (0, 1, 7):
+            gpu.synth_dev(buf, n, seed, off, dst_offset=dst_off)
+            assert np.array_equal(buf.download(n, offset=dst_off), O.synth(n, seed, off))
+
+
+# ------------------------------------------------------------------------------------------------ a1 grayscale
+def test_gray_golden_crop(gpu):
+    gpu.set_luma_mode("strict")
+    rgb, gold = png("test_crop_rgb.png"), png("test_crop_gray.png")
+    assert np.array_equal(gpu.convert_to_grayscale(rgb.copy()), gold)
+
+
+def test_gray_full_test_jpg(gpu, golden):
+    rgb = fixture_raw("test_rgb", golden["test_jpg"]["shape"])
+    if rgb is None:
+        pytest.skip("oracle/_ref/fixtures not built")
+    gpu.set_luma_mode("strict")
+    one = gpu.convert_to_grayscale(rgb.copy())
+    assert sha(one) == golden["test_jpg"]["golden_gray_sha256"]
+    two = gpu.convert_to_grayscale(one.copy())
+    assert sha(two) == golden["test_jpg"]["strict_p2_sha256"]
+    gpu.set_luma_mode("fma")
+    try:
+        assert sha(gpu.convert_to_grayscale(rgb.copy())) == golden["test_jpg"]["native_p1_sha256"]
+    finally:
+        gpu.set_luma_mode("strict")
+
+
+@pytest.mark.parametrize("h,w,seed", SYNTH_SHAPES)
+def test_gray_synthetic_shapes(gpu, O, golden, h, w, seed):
+    e = golden["synthetic"][f"{h}x{w}"]
+    rgb = O.synth(h * w * 3, 0xB2000000 + seed).reshape(h, w, 3)
+    rgba = O.synth(h * w * 4, 0xB2200000 + seed).reshape(h, w, 4)
+    for mode in ("strict", "fma"):
+        gpu.set_luma_mode(mode)
+        try:
+            got = gpu.convert_to_grayscale(rgb.copy())
+            assert sha(got) == e[f"gray_{mode}"]
+            assert np.array_equal(got, O.gray_inplace(rgb.copy(), 3, mode == "fma"))
+            got4 = gpu.convert_to_grayscale(rgba.copy())
+            assert np.array_equal(got4, O.gray_inplace(rgba.copy(), 4, mode == "fma"))
+            assert np.array_equal(got4[:, :, 3], rgba[:, :, 3])          # alpha untouched
+            if mode == "strict":
+                assert sha(got4) == e["gray_rgba_strict"]
+        finally:
+            gpu.set_luma_mode("strict")
+
+
+def test_gray_rejects_undefined_channel_counts(gpu):
+    for ch in (1, 2, 5):
+        with pytest.raises(gpu.OmpimgError):
+            gpu.convert_to_grayscale(np.zeros((4, 4, ch), np.uint8))
+
+
+@pytest.mark.parametrize("ch", [3, 4])
+@pytest.mark.parametrize("w,h,pitch_extra,nframes", [(640, 37, 0, 3), (333, 20, 9, 2), (1000, 8, 48, 4), (4096, 5, 128, 1), (16, 3, 0, 5)])
+def test_gray_device_pitched_batches(gpu, O, ch, w, h, pitch_extra, nframes):
+    """device-resident entry point: pitched rows, several frames, aligned (bulk) and unaligned (generic) layouts"""
+    row = w * ch
+    pitch = row + pitch_extra
+    src = O.synth(nframes * h * row, 77 + w + ch).reshape(nframes * h, row)
+    buf = to_dev_pitched(gpu, src, pitch)
+    ck(gpu, gpu.lib().ompimg_gray_inplace_dev(buf.ptr, pitch, w, h, ch, nframes, pitch * h, 0))
+    got = from_dev_pitched(gpu, buf, nframes * h, pitch, pitch)
+    want = O.gray_inplace(src.copy().reshape(nframes, h, w, ch), ch).reshape(nframes * h, row)
+    assert np.array_equal(got[:, :row], want)
+    assert np.all(got[:, row:] == 0xCD)                                  # padding untouched
+
+
+def test_rgb_to_luma_device(gpu, O):
+    for (w, h, ch) in [(1920, 16, 3), (1001, 7, 3), (512, 9, 4), (37, 5, 4)]:
+        rgb = O.synth(h * w * ch, 5 + w).reshape(h, w * ch)
+        rp, lp = (w * ch + 127) // 128 * 128, (w + 127) // 128 * 128
+        src = to_dev_pitched(gpu, rgb, rp)
+        dst = gpu.DeviceBuffer(lp * h + 64)
+        dst.fill(0xEE)
+        ck(gpu, gpu.lib().ompimg_rgb_to_luma_dev(src.ptr, rp, ch, dst.ptr, lp, w, h, 1, 0, 0, 0))
+        got = from_dev_pitched(gpu, dst, h, lp, lp)
+        assert np.array_equal(got[:, :w], O.rgb_to_luma(rgb.reshape(h, w, ch)))
+        assert np.all(got[:, w:] == 0xEE)
+
+
+# ------------------------------------------------------------------------------------------------ a2 Sobel
+@pytest.mark.parametrize("h,w,seed", SYNTH_SHAPES)
+def test_sobel_synthetic_shapes_border_untouched(gpu, O, golden, h, w, seed):
+    plane = O.synth(h * w, 0xB2100000 + seed).reshape(h, w)
+    pre = np.full((h, w), 0xAB, np.uint8)
+    got = gpu.sobel_edge(plane, pre.copy())
+    assert sha(got) == golden["synthetic"][f"{h}x{w}"]["sobel_prefill_ab"]
+    assert np.array_equal(got, O.sobel(plane, pre.copy()))
+
+
+@pytest.mark.parametrize("h,w", [(1, 1), (2, 9), (9, 2), (1, 40), (3, 3), (3, 17), (17, 3), (4, 513), (5, 1025), (16, 4097), (7, 8200)])
+def test_sobel_small_and_ragged(gpu, O, h, w):
+    rng = np.random.default_rng(h * 10007 + w)
+    plane = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    pre = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    assert np.array_equal(gpu.sobel_edge(plane, pre.copy()), O.sobel(plane, pre.copy()))
+
+
+def test_sobel_extreme_patterns(gpu, O):
+    h, w = 96, 1024 + 48
+    yy, xx = np.mgrid[0:h, 0:w]
+    pats = {
+        "step_v": np.where(xx >= w // 2, 255, 0), "step_h": np.where(yy >= h // 2, 255, 0),
+        "checker": ((xx + yy) & 1) * 255, "checker2": (((xx >> 1) + (yy >> 1)) & 1) * 255,
+        "white": np.full((h, w), 255), "ramp": (xx + yy) & 255, "stripes": (xx % 3 == 0) * 255,
+        "perfect_squares": np.where(xx >= w // 2, 60, 0) + np.where(yy >= h // 2, 45, 0),   # |g| = (3,4,5)-multiples
+    }
+    for name, p in pats.items():
+        plane = np.ascontiguousarray(p.astype(np.uint8))
+        assert np.array_equal(gpu.sobel_edge(plane), O.sobel(plane)), name
+
+
+@pytest.mark.parametrize("w,h,nframes,pitch_extra", [(1920, 40, 3, 0), (2000, 33, 2, 48), (333, 50, 4, 50), (4608, 12, 2, 0), (9000, 9, 1, 16)])
+def test_sobel_device_batches(gpu, O, w, h, nframes, pitch_extra):
+    sp = (w + 15) // 16 * 16 + pitch_extra if pitch_extra % 16 == 0 else w + pitch_extra
+    dp = sp
+    src = O.synth(nframes * h * w, 31 + w).reshape(nframes * h, w)
+    sbuf = to_dev_pitched(gpu, src, sp)
+    dbuf = gpu.DeviceBuffer(dp * h * nframes + 64)
+    dbuf.fill(0x77)
+    ck(gpu, gpu.lib().ompimg_sobel_dev(sbuf.ptr, sp, dbuf.ptr, dp, w, h, nframes, sp * h, dp * h, 0))
+    got = from_dev_pitched(gpu, dbuf, nframes * h, dp, dp)
+    for f in range(nframes):
+        want = O.sobel(np.ascontiguousarray(src[f * h:(f + 1) * h]), np.full((h, w), 0x77, np.uint8))
+        assert np.array_equal(got[f * h:(f + 1) * h, :w], want), f
+    assert np.all(got[:, w:] == 0x77)
+
+
+# ------------------------------------------------------------------------------------------------ a3..a5 fused
+@pytest.mark.parametrize("variant", ["strict", "fma"])
+def test_gray_sobel_pass_golden_crop(gpu, variant):
+    gpu.set_luma_mode(variant)
+    try:
+        rgb, want = png("photo_crop_rgb.png"), png(f"photo_crop_edge_{variant}.png")
+        got, _ = gpu.gray_sobel_pass(rgb.copy())
+        assert np.array_equal(got, want)
+    finally:
+        gpu.set_luma_mode("strict")
+
+
+def test_gray_sobel_pass_full_photo_two_passes(gpu, golden):
+    """BASELINE config 2: the Sobel driver on images/more_than_one_mega_photo.jpg, passes = 1 and 2."""
+    rgb = fixture_raw("photo_rgb", golden["photo_jpg"]["shape"])
+    if rgb is None:
+        pytest.skip("oracle/_ref/fixtures not built")
+    h, w, _ = rgb.shape
+    edge = np.zeros((h, w), np.uint8)                 # the driver's malloc'ed scratch: zero pages in practice
+    img, edge = gpu.gray_sobel_pass(rgb.copy(), edge)
+    assert sha(img) == golden["photo_jpg"]["strict_p1_sha256"]
+    img2, _ = gpu.gray_sobel_pass(img.copy(), edge)
+    assert sha(img2) == golden["photo_jpg"]["strict_p2_sha256"]
+    gpu.set_luma_mode("fma")
+    try:
+        assert sha(gpu.gray_sobel_pass(rgb.copy())[0]) == golden["photo_jpg"]["native_p1_sha256"]
+    finally:
+        gpu.set_luma_mode("strict")
+
+
+def test_gray_sobel_pass_half_photo_odd_pitch(gpu, golden):
+    rgb = fixture_raw("half_rgb", golden["half_jpg"]["shape"])      # 2037 wide: no 16-byte friendly pitch
+    if rgb is None:
+        pytest.skip("oracle/_ref/fixtures not built")
+    assert sha(gpu.gray_sobel_pass(rgb.copy())[0]) == golden["half_jpg"]["strict_p1_sha256"]
+
+
+@pytest.mark.parametrize("h,w,seed", SYNTH_SHAPES)
+def test_gray_sobel_pass_synthetic_shapes(gpu, O, golden, h, w, seed):
+    e = golden["synthetic"][f"{h}x{w}"]
+    rgb = O.synth(h * w * 3, 0xB2000000 + seed).reshape(h, w, 3)
+    for mode in ("strict", "fma"):
+        gpu.set_luma_mode(mode)
+        try:
+            got, _ = gpu.gray_sobel_pass(rgb.copy())
+            assert sha(got) == e[f"pass_{mode}"]
+        finally:
+            gpu.set_luma_mode("strict")
+    # scratch plane border survives and is replicated (main_with_sobel.c:37, :65-73)
+    edge = np.full((h, w), 0x3C, np.uint8)
+    got, edge_out = gpu.gray_sobel_pass(rgb.copy(), edge)
+    want_img, want_edge = O.gray_sobel_pass(rgb.copy(), np.full((h, w), 0x3C, np.uint8))
+    assert np.array_equal(got, want_img) and np.array_equal(edge_out, want_edge)
+
+
+@pytest.mark.parametrize("ch", [3, 4])
+@pytest.mark.parametrize("w,h,nframes", [(3840, 24, 2), (1920, 30, 3), (2000, 19, 2), (4200, 10, 2), (8200, 7, 1), (100, 40, 3), (16, 5, 2)])
+def test_rgb_to_edge_device_batches(gpu, O, ch, w, h, nframes):
+    row = w * ch
+    rp, ep = (row + 127) // 128 * 128, (w + 127) // 128 * 128
+    src = O.synth(nframes * h * row, 900 + w + ch).reshape(nframes * h, row)
+    sbuf = to_dev_pitched(gpu, src, rp)
+    dbuf = gpu.DeviceBuffer(ep * h * nframes + 64)
+    dbuf.fill(0x11)
+    ck(gpu, gpu.lib().ompimg_rgb_to_edge_dev(sbuf.ptr, rp, ch, dbuf.ptr, ep, w, h, nframes, rp * h, ep * h, 0))
+    got = from_dev_pitched(gpu, dbuf, nframes * h, ep, ep)
+    for f in range(nframes):
+        frame = np.ascontiguousarray(src[f * h:(f + 1) * h]).reshape(h, w, ch)
+        want = O.rgb_to_edge(frame, np.full((h, w), 0x11, np.uint8))
+        assert np.array_equal(got[f * h:(f + 1) * h, :w], want), f
+    assert np.all(got[:, w:] == 0x11)
+
+
+def test_rgb_to_edge_unaligned_generic_path(gpu, O):
+    w, h, ch = 333, 21, 3
+    src = O.synth(h * w * ch, 4242).reshape(h, w * ch)
+    sbuf = to_dev_pitched(gpu, src, w * ch)                 # dense, pitch 999: not a multiple of 16
+    dbuf = gpu.DeviceBuffer(w * h + 64)
+    dbuf.fill(0)
+    ck(gpu, gpu.lib().ompimg_rgb_to_edge_dev(sbuf.ptr, w * ch, ch, dbuf.ptr, w, w, h, 1, 0, 0, 0))
+    assert np.array_equal(from_dev_pitched(gpu, dbuf, h, w, w), O.rgb_to_edge(src.reshape(h, w, ch)))
+
+
+def test_rgb_to_edge_batch_host(gpu, O):
+    """BASELINE config 3 shape (3840x2160 RGB frames), a small batch through the pipelined host API."""
+    n, h, w = 5, 2160, 3840
+    frames = O.synth(n * h * w * 3, 0xB2000003).reshape(n, h, w, 3)
+    got = gpu.rgb_to_edge_batch(frames)
+    for f in (0, n - 1):
+        assert np.array_equal(got[f], O.rgb_to_edge(frames[f]))
+    small = O.synth(11 * 50 * 70 * 3, 99).reshape(11, 50, 70, 3)      # more frames than streams, odd pitch
+    got = gpu.rgb_to_edge_batch(small)
+    for f in range(11):
+        assert np.array_equal(got[f], O.rgb_to_edge(small[f]))
+
+
+def test_row_bands_equal_single_pass(gpu, O):
+    """Row-band decomposition (BASELINE config 5) is bit-identical to the whole-image result; the bands
+    here live on one device, so the halo pointers are exercised without needing a second GPU."""
+    w, h = 1500, 257
+    rgb = O.synth(h * w * 3, 0xB2000005).reshape(h, w, 3)
+    want = O.rgb_to_edge(rgb)
+    for ndev in (1, 2, 3, 8):
+        b = gpu.Bands(w, h, 3, [0] * ndev)
+        b.upload(rgb)
+        b.rgb_to_edge()
+        got = b.download_edge()
+        assert np.array_equal(got, want), ndev
+        assert b.checksum() == int(want[1:-1, 1:-1].astype(np.int64).sum())
+        b.close()
+    b = gpu.Bands(w, h, 3, [0, 0])
+    b.synth(0xB2000005)
+    b.rgb_to_edge()
+    assert np.array_equal(b.download_edge(), want)
+    b.close()
+
+
+# ------------------------------------------------------------------------------------------------ old/ kernels
+@pytest.mark.parametrize("key", ["37_53_5_273", "64_96_9_81", "24_31_3_16", "48_40_5_25"])
+def test_old_kernels_golden(gpu, O, golden, key):
+    rows, cols, K, norm = map(int, key.split("_"))
+    e = golden["old"][key]
+    padded = O.synth((rows + K - 1) * (cols + K - 1) * 3, 0xB2300000 + e["seed"]).reshape(rows + K - 1, cols + K - 1, 3)
+    kern = np.array(e["kernel"], np.int64).reshape(K, K)
+    out = gpu.parallel_convolution(padded, kern, norm)
+    assert sha(out.astype(np.int64)) == e["conv_sha256_i64"]
+    img = np.ascontiguousarray(padded[:rows, :cols])
+    assert gpu.parallel_avg_pixel(img).tolist() == e["avg"]
+    g3, mm = gpu.parallel_to_grayscale(img)
+    assert sha(g3.astype(np.int64)) == e["gray3_sha256_i64"] and mm.tolist() == e["minmax"]
+
+
+@pytest.mark.parametrize("K,kind", [(3, "rand"), (5, "box"), (5, "gauss"), (5, "rand"), (7, "rand"), (9, "box"), (9, "gauss"), (9, "rand"),
+                                    (4, "rand"), (11, "box"), (2, "rand"), (1, "rand")])
+def test_convolution_vs_oracle(gpu, O, K, kind):
+    rows, cols = 131, 517
+    rng = np.random.default_rng(K * 31 + len(kind))
+    padded = O.synth((rows + K - 1) * (cols + K - 1) * 3, 0xC0 + K).reshape(rows + K - 1, cols + K - 1, 3)
+    if kind == "box":
+        kern, norm = np.ones((K, K), np.int64), K * K
+    elif kind == "gauss":
+        b = np.array([1.0]);
+        for _ in range(K - 1):
+            b = np.convolve(b, [1, 1])
+        kern = np.outer(b, b).astype(np.int64); norm = int(kern.sum())
+    else:
+        kern, norm = rng.integers(-9, 10, (K, K)).astype(np.int64), int(rng.integers(1, 50)) * (1 if K % 2 else -1)
+    assert np.array_equal(gpu.parallel_convolution(padded, kern, norm), O.convolution_u8(padded, kern, norm))
+
+
+def test_avg_and_gray3_accumulate_and_ragged(gpu, O):
+    for (rows, cols) in [(1, 1), (7, 5), (33, 100), (240, 1001), (1080, 1920)]:
+        img = O.synth(rows * cols * 3, rows + cols).reshape(rows, cols, 3)
+        assert gpu.parallel_avg_pixel(img, (5, 900, 12345)).tolist() == O.avg_pixel_u8(img, (5, 900, 12345)).tolist()
+        g, mm = gpu.parallel_to_grayscale(img)
+        wg, wmm = O.gray_avg3_u8(img)
+        assert np.array_equal(g, wg) and mm.tolist() == wmm.tolist()
+    const = np.full((9, 9, 3), 200, np.uint8)
+    assert gpu.parallel_to_grayscale(const)[1].tolist() == [200, 200]
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_batch_properties(gpu, O):
+    """cfg3 at full frame size on the device-resident path: a batch made of copies of two distinct frames
+    must give copies of the two oracle results (checksum of checksums), wherever the frame sits in the batch."""
+    L = gpu.lib()
+    w, h, n = 3840, 2160, 24
+    fb, eb = w * h * 3, w * h
+    a = O.synth(fb, 0xB2000003)
+    b = O.synth(fb, 0xB2000013)
+    src = gpu.DeviceBuffer(n * fb)
+    for f in range(n):
+        src.upload(a if f % 3 else b, offset=f * fb)
+    dst = gpu.DeviceBuffer(n * eb)
+    dst.fill(0)
+    ck(gpu, L.ompimg_rgb_to_edge_dev(src.ptr, w * 3, 3, dst.ptr, w, w, h, n, fb, eb, 0))
+    gpu.sync(0)
+    ea, eb_ = O.rgb_to_edge(a.reshape(h, w, 3)), O.rgb_to_edge(b.reshape(h, w, 3))
+    for f in range(n):
+        got = dst.download(eb, offset=f * eb).reshape(h, w)
+        assert np.array_equal(got, ea if f % 3 else eb_), f
+    # in-place grayscale of the same batch, twice: pass 2 is the reference's fixed point behaviour
+    ck(gpu, L.ompimg_gray_inplace_dev(src.ptr, w * 3, w, h, 3, n, fb, 0))
+    gpu.sync(0)
+    ga = O.gray_inplace(a.copy().reshape(h, w, 3), 3)
+    assert np.array_equal(src.download(fb, offset=1 * fb).reshape(h, w, 3), ga)
+    ck(gpu, L.ompimg_gray_inplace_dev(src.ptr, w * 3, w, h, 3, n, fb, 0))
+    gpu.sync(0)
+    assert np.array_equal(src.download(fb, offset=(n - 1) * fb).reshape(h, w, 3), O.gray_inplace(ga.copy(), 3))
+
+
+def test_full_size_convolution_box_property(gpu, O):
+    """cfg4 (8192x8192 RGB): a box blur of a constant image is the constant, and a 5x5 box on synthetic
+    data matches the oracle on a sampled window (the oracle on the full image takes too long for CI)."""
+    L = gpu.lib()
+    rows = cols = 8192
+    for K in (5, 9):
+        pr, pc = rows + K - 1, cols + K - 1
+        src = gpu.DeviceBuffer(pr * pc * 3)
+        gpu.synth_dev(src, pr * pc * 3, 0xB2000004)
+        out = gpu.DeviceBuffer(rows * cols * 3)
+        taps = np.ones(K * K, np.int32)
+        ck(gpu, L.ompimg_conv_u8_dev(src.ptr, pc * 3, rows, cols, K, taps.ctypes.data, K * K, out.ptr, cols * 3, 0))
+        gpu.sync(0)
+        y0, x0, hh, ww = 4001, 3001, 40, 64
+        win = np.stack([src.download((ww + K - 1) * 3, offset=((y0 + r) * pc + x0) * 3) for r in range(hh + K - 1)]).reshape(hh + K - 1, ww + K - 1, 3)
+        want = O.convolution_u8(win, np.ones((K, K), np.int64), K * K).astype(np.uint8)
+        got = np.stack([out.download(ww * 3, offset=((y0 + r) * cols + x0) * 3) for r in range(hh)]).reshape(hh, ww, 3)
+        assert np.array_equal(got, want)
+        src.free(); out.free()
