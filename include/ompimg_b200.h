@@ -66,6 +66,7 @@ OMPIMG_API const char *ompimg_last_error(void);
 OMPIMG_API const char *ompimg_version(void);
 OMPIMG_API int         ompimg_set_luma_mode(int mode);     /* OMPIMG_LUMA_* */
 OMPIMG_API int         ompimg_get_luma_mode(void);
+OMPIMG_API int         ompimg_sqrt_is_exact(void);   /* 1: the device passed the exhaustive sqrt check at init (no +0.5 guard in the Sobel kernels), 0: guard in use, -1: not initialised */
 OMPIMG_API long long   ompimg_launch_count(void);          /* kernels launched by this library so far */
 OMPIMG_API int         ompimg_shutdown(void);
 
@@ -173,8 +174,9 @@ OMPIMG_API int ompimg_synth_fill_dev(uint8_t *dst, unsigned long long nbytes, un
 /* ---- self tests used by tests/ (device arithmetic against closed forms) --------------------------- */
 /* lut[(r<<16)|(g<<8)|b] = luma(r,g,b) for all 2^24 triples, written to HOST memory */
 OMPIMG_API int ompimg_selftest_luma_lut(uint8_t *lut_host, int mode);
-/* out[m] = the kernel's min(255, isqrt(m)) for m in [0, count): HOST memory */
-OMPIMG_API int ompimg_selftest_isqrt(uint8_t *out_host, unsigned int count);
+/* out[m] = sat_u8(trunc(sqrt.approx(m + bias))) as the Sobel kernels compute it (bias 0.5 is the guard the
+ * kernels use; it must equal min(255, isqrt(m)) for every m): HOST memory */
+OMPIMG_API int ompimg_selftest_isqrt(uint8_t *out_host, unsigned int count, float bias);
 
 /* ---- row-band decomposition of one large image over several devices of this process -------------
  * (BASELINE config 5).  The image is split into `ndev` bands of rows; each device holds its band

@@ -60,6 +60,7 @@ _SIGS = {
     "ompimg_version": (C.c_char_p, []),
     "ompimg_set_luma_mode": (C.c_int, [C.c_int]),
     "ompimg_get_luma_mode": (C.c_int, []),
+    "ompimg_sqrt_is_exact": (C.c_int, []),
     "ompimg_launch_count": (C.c_longlong, []),
     "ompimg_shutdown": (C.c_int, []),
     "ompimg_dev_alloc": (_vp, [_sz]),
@@ -101,7 +102,7 @@ _SIGS = {
     "ompimg_gray_avg3_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
     "ompimg_synth_fill_dev": (C.c_int, [_vp, C.c_ulonglong, C.c_uint, C.c_ulonglong, C.c_int]),
     "ompimg_selftest_luma_lut": (C.c_int, [_vp, C.c_int]),
-    "ompimg_selftest_isqrt": (C.c_int, [_vp, C.c_uint]),
+    "ompimg_selftest_isqrt": (C.c_int, [_vp, C.c_uint, C.c_float]),
     "ompimg_bands_create": (_vp, [C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "ompimg_bands_destroy": (C.c_int, [_vp]),
     "ompimg_bands_rows": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -325,9 +326,9 @@ def luma_lut(mode: int | str = LUMA_STRICT) -> np.ndarray:
     return lut
 
 
-def isqrt_table(count: int) -> np.ndarray:
+def isqrt_table(count: int, bias: float = 0.5) -> np.ndarray:
     out = np.empty(count, np.uint8)
-    _ck(lib().ompimg_selftest_isqrt(_ptr(out), count), "selftest_isqrt")
+    _ck(lib().ompimg_selftest_isqrt(_ptr(out), count, bias), "selftest_isqrt")
     return out
 
 

@@ -195,6 +195,7 @@ extern "C" int ompimg_bands_rgb_to_edge(ompimg_bands *b, float *ms_max) {
         a.src = b->rgb[i]; a.dst = b->edge[i]; a.src_pitch = b->rpitch; a.dst_pitch = b->epitch;
         a.width = b->w; a.height = rows; a.channels = b->ch; a.nframes = 1; a.fma_mode = mode;
         a.halo_above = above; a.halo_below = below;
+        a.no_bias = sqrt_exact_flag();
         BCK(launch_sobel(a, b->sm_count[i], b->st[i]));
         BCK(cudaEventRecord(b->e1[i], b->st[i]));
     }

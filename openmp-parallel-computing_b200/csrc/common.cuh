@@ -29,6 +29,10 @@ __device__ __forceinline__ void unpack64(u64 v, uint32_t &lo, uint32_t &hi) {
 }
 __device__ __forceinline__ u64 splat2(float x) { return pack64(__float_as_uint(x), __float_as_uint(x)); }
 
+// pin a loop-invariant value in a register (ptxas cannot rematerialise what it cannot see through)
+__device__ __forceinline__ uint32_t keep(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
+__device__ __forceinline__ u64 keep64(u64 x) { asm volatile("" : "+l"(x)); return x; }
+
 // packed fp32 pairs (one issue slot for two pixels)
 __device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
     u64 d;
@@ -292,6 +296,30 @@ __device__ __forceinline__ void store_partial16(uint8_t *dst, uint4 v, int first
 #pragma unroll
     for (int i = 0; i < 16; ++i)
         if (i >= first && i < last) dst[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+}
+
+// the two border cases of a 16-byte output group, with few wide stores instead of 16 byte stores
+//   mode 2: the group holds x == 0          -> bytes 1..15
+//   mode 3: the group holds x == width-1    -> bytes 0..plast-1 (plast in 0..15)
+//   mode 4: both (image narrower than 17)   -> byte loop
+static __device__ __noinline__ void store_edge16(uint8_t *q, uint4 o, int mode, int plast) {
+    if (mode == 2) {
+        q[1] = (uint8_t)(o.x >> 8);
+        *reinterpret_cast<uint16_t *>(q + 2) = (uint16_t)(o.x >> 16);
+        *reinterpret_cast<uint32_t *>(q + 4) = o.y;
+        *reinterpret_cast<uint2 *>(q + 8) = make_uint2(o.z, o.w);
+    } else if (mode == 3) {
+        const int n = plast;
+        if (n & 8) *reinterpret_cast<uint2 *>(q) = make_uint2(o.x, o.y);
+        uint32_t w = (n & 8) ? o.z : o.x;
+        const uint32_t wn = (n & 8) ? o.w : o.y;
+        int pos = n & 8;
+        if (n & 4) { *reinterpret_cast<uint32_t *>(q + pos) = w; pos += 4; w = wn; }
+        if (n & 2) { *reinterpret_cast<uint16_t *>(q + pos) = (uint16_t)w; pos += 2; w >>= 16; }
+        if (n & 1) q[pos] = (uint8_t)w;
+    } else {
+        store_partial16(q, o, 1, plast);
+    }
 }
 
 }  // namespace ompimg

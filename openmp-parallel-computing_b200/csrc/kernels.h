@@ -53,9 +53,11 @@ struct StencilArgs {
     const uint8_t *halo_above;   // address of source row (row0-1), or nullptr
     const uint8_t *halo_below;   // address of source row (row0+height), or nullptr
     int row0, full_height;
+    int no_bias;                 // 1: MUFU.SQRT was validated exact on this device, skip the +0.5 guard (runtime.cu)
 };
 cudaError_t launch_sobel(const StencilArgs &a, int sm_count, cudaStream_t st);
-cudaError_t launch_isqrt_selftest(uint8_t *out_dev, unsigned int count, cudaStream_t st);
+int sqrt_exact_flag();          // runtime.cu: 1 when the bound device passed the exhaustive MUFU.SQRT check
+cudaError_t launch_isqrt_selftest(uint8_t *out_dev, unsigned int count, float bias, cudaStream_t st);
 
 // conv.cu -----------------------------------------------------------------------------------------
 cudaError_t launch_conv(const uint8_t *in, size_t in_pitch, int rows, int cols, int K, const int32_t *taps_host, int32_t norm,

@@ -34,6 +34,7 @@ struct Ctx {
     int device = -1;
     int sm_count = 0;
     int luma_mode = OMPIMG_LUMA_STRICT;
+    int sqrt_exact = 0;                      // MUFU.SQRT validated over every reachable gx^2+gy^2 on this device
     cudaStream_t streams[OMPIMG_NUM_STREAMS] = {};
     cudaEvent_t edge_events[OMPIMG_NUM_STREAMS] = {};
     std::vector<Timer> timers;
@@ -153,7 +154,29 @@ extern "C" int ompimg_init(int device) {
     if (m) g.luma_mode = (!strcmp(m, "fma") || !strcmp(m, "1")) ? OMPIMG_LUMA_FMA : OMPIMG_LUMA_STRICT;
     g.device = device;
     g.ready = true;
+    // The Sobel kernels truncate sqrt.approx(m).  Whether that equals isqrt(m) at the perfect squares
+    // depends on the MUFU.SQRT unit, so it is checked here once, exhaustively, for every m that
+    // gx^2+gy^2 can take; the kernels add a +0.5 guard (one more instruction per pixel) unless the
+    // check passes.  OMPIMG_SQRT_GUARD=1 keeps the guard regardless.
+    g.sqrt_exact = 0;
+    const char *guard = getenv("OMPIMG_SQRT_GUARD");
+    if (!(guard && atoi(guard) != 0)) {
+        const unsigned int n = 2u * 1020u * 1020u + 1u;
+        std::vector<uint8_t> tab(n);
+        if (ompimg_selftest_isqrt(tab.data(), n, 0.0f) == OMPIMG_OK) {
+            bool ok = true;
+            unsigned int r = 0;                       // floor(sqrt(m)), advanced incrementally
+            for (unsigned int m = 0; m < n && ok; ++m) {
+                if ((r + 1) * (r + 1) <= m) ++r;
+                ok = tab[m] == (r > 255u ? 255u : r);
+            }
+            g.sqrt_exact = ok ? 1 : 0;
+        }
+    }
     return OMPIMG_OK;
+}
+namespace ompimg {
+int sqrt_exact_flag() { return g.ready ? g.sqrt_exact : 0; }
 }
 extern "C" int ompimg_device(void) { return g.ready ? g.device : -1; }
 extern "C" int ompimg_device_count(void) {
@@ -170,6 +193,7 @@ extern "C" int ompimg_set_luma_mode(int mode) {
     return OMPIMG_OK;
 }
 extern "C" int ompimg_get_luma_mode(void) { return g.luma_mode; }
+extern "C" int ompimg_sqrt_is_exact(void) { return g.ready ? g.sqrt_exact : -1; }
 extern "C" long long ompimg_launch_count(void) { return g_launch_count.load(); }
 extern "C" int ompimg_shutdown(void) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
@@ -320,6 +344,7 @@ static int sobel_common(const uint8_t *src, size_t sp, int ch, uint8_t *dst, siz
     a.src = src; a.dst = dst; a.src_pitch = sp; a.dst_pitch = dp; a.src_stride = ss; a.dst_stride = ds;
     a.width = w; a.height = h; a.channels = ch; a.nframes = nframes; a.fma_mode = g.luma_mode;
     a.halo_above = above; a.halo_below = below;
+    a.no_bias = g.sqrt_exact;
     CK(launch_sobel(a, g.sm_count, st));
     return OMPIMG_OK;
 }
@@ -411,12 +436,12 @@ extern "C" int ompimg_selftest_luma_lut(uint8_t *lut_host, int mode) {
     CK(cudaStreamSynchronize(g.streams[0]));
     return OMPIMG_OK;
 }
-extern "C" int ompimg_selftest_isqrt(uint8_t *out_host, unsigned int count) {
+extern "C" int ompimg_selftest_isqrt(uint8_t *out_host, unsigned int count, float bias) {
     INIT();
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     NEED(out_host && count > 0, "out");
     RESERVE(g.scratch[0], count);
-    CK(launch_isqrt_selftest((uint8_t *)g.scratch[0].p, count, g.streams[0]));
+    CK(launch_isqrt_selftest((uint8_t *)g.scratch[0].p, count, bias, g.streams[0]));
     CK(cudaMemcpyAsync(out_host, g.scratch[0].p, count, cudaMemcpyDeviceToHost, g.streams[0]));
     CK(cudaStreamSynchronize(g.streams[0]));
     return OMPIMG_OK;

@@ -41,7 +41,7 @@ __device__ __forceinline__ void load_group_words(uint32_t addr, uint32_t (&w)[4 
     }
 }
 
-template <int CH, int FMA_MODE>
+template <int CH, int FMA_MODE, bool BIAS>
 __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32) sobel_rows_kernel(const StencilParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int BPP = CH;                      // bytes per source pixel
@@ -78,8 +78,9 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32) sobel_rows_kernel(const 
         const uint32_t dst_off = xs == 0 ? 16u : 0u;
         int s = 0;
         uint32_t ph = 0;
-        for (int i = 0; i < nin; ++i) {
-            const int r = rin0 + i;
+        const int nin_even = (nin + 1) & ~1;      // consumers take rows two at a time
+        for (int i = 0; i < nin_even; ++i) {
+            const int r = min(rin0 + i, rin1);
             if (i >= S) mbar_wait(empty0 + 8 * s, ph ^ 1);
             const uint32_t d = smem0 + s * p.stage_bytes + dst_off;
             if (r >= 0 && r < p.height) {
@@ -103,31 +104,75 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32) sobel_rows_kernel(const 
     }
 
     // ---------------------------------------------------------------------- consumer warps
+    // Everything loop-invariant is computed once and pinned in a register with keep(): ptxas
+    // otherwise rematerialises these values (S2R + LDC + integer math) inside the row loop, and
+    // this kernel is bound by issue slots, not by registers.
     const int c = warp * 32 + lane;               // 16-pixel group index inside the strip
     const int x0 = xs + 16 * c;
-    const bool active = x0 < p.width;
-    const bool full_store = x0 >= 16 && x0 + 16 <= p.width - 1;
-    const int pfirst = x0 == 0 ? 1 : 0, plast = min(16, p.width - 1 - x0);
-    const uint32_t goff = 16u + (uint32_t)c * (16u * BPP);
-    float half = 0.5f;
-    asm volatile("" : "+f"(half));                // keep 0.5 in a register (FHFMA takes no immediate addend)
-
-    SobelRowState st[8];
+    // how this lane stores its 16 output bytes: 0 nothing, 1 one 16-byte store, 2 group holds x == 0,
+    // 3 group holds x == width-1 (and possibly bytes past the row), 4 both (very narrow images)
+    int mode = 0;
+    if (x0 < p.width) {
+        const bool l = x0 == 0, r = x0 + 16 > p.width - 1;
+        mode = l ? (r ? 4 : 2) : (r ? 3 : 1);
+    }
+    mode = (int)keep((uint32_t)mode);
+    const int plast = min(16, p.width - 1 - x0);  // valid bytes are [x0 == 0, plast)
+    const uint32_t my = keep(smem0 + 16u + (uint32_t)c * (16u * BPP));
+    const uint32_t stage_bytes = keep(p.stage_bytes);
+    const uint32_t ring_bytes = keep((uint32_t)S * p.stage_bytes);
+    const uint32_t eoff = keep(8u * (uint32_t)S);
+    const uint32_t fb0 = keep(full0);
+    const uint32_t lane0 = keep(lane == 0 ? 1u : 0u);
+    const uint32_t ncons = keep((uint32_t)NW * 32u);
+    const bool multi_strip = gridDim.y > 1;
+    // warp-edge luma exchange: lane 0 publishes its first luma, lane 31 its last one, every other lane
+    // writes to a scratch word; lane 0 / 31 of an inner warp read the neighbour warp's value, selected
+    // with a mask instead of a branch
+    const uint32_t dummy0 = edge0 + 2u * (uint32_t)NW * 8u;
+    const uint32_t ex_par = (uint32_t)NW * 8u;
+    const uint32_t exw = edge0 + (uint32_t)warp * 8u;
+    uint32_t stsA[2], stsB[2], ldsL[2], ldsR[2];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) st[k].sab = st[k].dhb = st[k].sha = st[k].shb = 0u;
+    for (int par = 0; par < 2; ++par) {
+        stsA[par] = keep(lane == 0 ? exw + par * ex_par : dummy0 + 4u * lane);
+        stsB[par] = keep(lane == 31 ? exw + par * ex_par + 4u : dummy0 + 128u + 4u * lane);
+        ldsL[par] = keep(exw + par * ex_par - 4u);
+        ldsR[par] = keep(exw + par * ex_par + 8u);
+    }
+    const uint32_t mL = keep((lane == 0 && warp > 0) ? 0xffffffffu : 0u);
+    const uint32_t mR = keep((lane == 31 && warp < NW - 1) ? 0xffffffffu : 0u);
+    const size_t dpitch = keep64(p.dst_pitch);
+    uint8_t *out = dst + (size_t)rin0 * p.dst_pitch + x0;     // row of the stage being consumed; stores go one row up
+    float half = BIAS ? 0.5f : 0.0f;
+    if (BIAS) asm volatile("" : "+f"(half));
 
-    int s = 0;
+    uint32_t sab[8], dhb[8], shX[8], shY[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sab[k] = dhb[k] = shX[k] = shY[k] = 0u;
+
+    uint32_t so = 0;                 // byte offset of the current stage in the ring
+    uint32_t fb = fb0;               // its full barrier (the empty barrier sits 8*S bytes above)
     uint32_t ph = 0;
-    for (int i = 0; i < nin; ++i) {
-        const uint32_t stage = smem0 + s * p.stage_bytes;
-        mbar_wait(full0 + 8 * s, ph);
+
+    // Rows are consumed two per trip so that the roles of the two Sh' register sets alternate
+    // without copies: A holds Sh' of the oldest row on entry and of the newest row on exit.
+    // (an odd row count is padded with one dummy row whose result is not stored; the producer
+    // re-sends the last row for it)
+    for (int i = 0; i < nin; i += 2) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const bool emit = i >= 2 && (hh == 0 || i + 1 < nin);   // the first two rows only prime the row state
+        uint32_t (&A)[8] = hh ? shY : shX;
+        const uint32_t stage = my + so;
+        mbar_wait(fb, ph);
         uint32_t P[8], Q[9];
         if (CH == 1) {
             const uint32_t C64 = 0x64646464u;
-            const uint4 v = lds128(stage + goff);
-            const uint32_t lw = lds32(stage + goff - 4), rw = lds32(stage + goff + 16);
+            const uint4 v = lds128(stage);
+            const uint32_t lw = lds32(stage - 4), rw = lds32(stage + 16);
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty0 + 8 * s);
+            if (lane0) mbar_arrive(fb + eoff);
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -135,36 +180,36 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32) sobel_rows_kernel(const 
                 P[2 * j + 1] = prmt(w[j], C64, 0x4342);
                 Q[2 * j + 1] = prmt(w[j], C64, 0x4241);
             }
-            Q[0] = prmt(prmt(lw, C64, 0x4342), P[0], 0x5432);
+            Q[0] = (prmt(lw, w[0], 0x0403) & 0x00ff00ffu) | 0x64006400u;      // (lw.b3, w0.b0) + f16 exponents: PRMT + LOP3
 #pragma unroll
             for (int j = 1; j < 4; ++j) Q[2 * j] = prmt(P[2 * j - 1], P[2 * j], 0x5432);
-            Q[8] = prmt(P[7], prmt(rw, C64, 0x4140), 0x5432);
+            Q[8] = (prmt(w[3], rw, 0x0403) & 0x00ff00ffu) | 0x64006400u;
         } else {
             uint32_t w[4 * CH];
-            load_group_words<CH>(stage + goff, w);
-            // strip-edge halo pixels (only when the image is wider than one strip)
+            load_group_words<CH>(stage, w);
             uint32_t eL = 0, eR = 0;
-            const bool needL = warp == 0 && lane == 0 && xs > 0;
-            const bool needR = warp == NW - 1 && lane == 31 && xs + SW < p.width;
-            if (needL) eL = lds32(stage + 16 - 4) >> (8 * (4 - BPP));                    // bytes of pixel xs-1 in the low lanes
-            if (needR) eR = lds32(stage + 16 + (uint32_t)SW * BPP);
+            if (multi_strip) {       // strip-edge pixels xs-1 and xs+SW (images wider than one strip only)
+                eL = lds32(smem0 + so + 12) >> (8 * (4 - BPP));
+                eR = lds32(smem0 + so + 16 + (uint32_t)SW * BPP);
+            }
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty0 + 8 * s);
+            if (lane0) mbar_arrive(fb + eoff);
             uint32_t f[16];
             const float MAGIC = 14942208.0f;      // 2^23 + 0x640000: result bits 0x4B6400ll
             if (CH == 3) luma16_rgb<FMA_MODE>(reinterpret_cast<const uint32_t(&)[12]>(w), f, MAGIC);
             else luma16_rgba<FMA_MODE>(reinterpret_cast<const uint32_t(&)[16]>(w), f, MAGIC);
-            // one luma per warp edge per row goes through shared memory, double-buffered by row parity
-            const uint32_t ex = edge0 + (uint32_t)(i & 1) * (NW * 8);
-            if (lane == 0) sts32(ex + warp * 8, f[0]);
-            if (lane == 31) sts32(ex + warp * 8 + 4, f[15]);
-            named_bar_sync(1, NW * 32);
+            sts32(stsA[hh], f[0]);
+            sts32(stsB[hh], f[15]);
+            named_bar_sync(1, ncons);
             uint32_t fL = __shfl_up_sync(0xffffffffu, f[15], 1);
             uint32_t fR = __shfl_down_sync(0xffffffffu, f[0], 1);
-            if (lane == 0 && warp > 0) fL = lds32(ex + (warp - 1) * 8 + 4);
-            if (lane == 31 && warp < NW - 1) fR = lds32(ex + (warp + 1) * 8);
-            if (needL) fL = 0x4B640000u | luma1<FMA_MODE>(eL & 255u, (eL >> 8) & 255u, (eL >> 16) & 255u);
-            if (needR) fR = 0x4B640000u | luma1<FMA_MODE>(eR & 255u, (eR >> 8) & 255u, (eR >> 16) & 255u);
+            const uint32_t nL = lds32(ldsL[hh]), nR = lds32(ldsR[hh]);
+            fL = (nL & mL) | (fL & ~mL);
+            fR = (nR & mR) | (fR & ~mR);
+            if (multi_strip) {
+                if (warp == 0 && lane == 0 && xs > 0) fL = 0x4B640000u | luma1<FMA_MODE>(eL & 255u, (eL >> 8) & 255u, (eL >> 16) & 255u);
+                if (warp == NW - 1 && lane == 31 && xs + SW < p.width) fR = 0x4B640000u | luma1<FMA_MODE>(eR & 255u, (eR >> 8) & 255u, (eR >> 16) & 255u);
+            }
 #pragma unroll
             for (int k = 0; k < 8; ++k) P[k] = prmt(f[2 * k], f[2 * k + 1], 0x6420);
             Q[0] = prmt(fL, f[0], 0x6420);
@@ -174,14 +219,28 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32) sobel_rows_kernel(const 
         }
         uint32_t gx[8], gy[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) sobel_pair(P[k], Q[k], Q[k + 1], st[k], gx[k], gy[k]);
-        if (i >= 2 && active) {
-            const uint4 o = sobel_mag16(gx, gy, half);
-            uint8_t *out = dst + (size_t)(rin0 + i - 1) * p.dst_pitch + x0;
-            if (full_store) *reinterpret_cast<uint4 *>(out) = o;
-            else store_partial16(out, o, pfirst, plast);
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t dh = hsub2(Q[k + 1], Q[k]);
+            const uint32_t t1 = hfma2(P[k], 0x40004000u /*2,2*/, 0xEA00EA00u /*-3072,-3072*/);
+            const uint32_t sh = hadd2(hadd2(t1, Q[k]), Q[k + 1]);
+            const uint32_t sbc = hadd2(dhb[k], dh);
+            gx[k] = hadd2(sab[k], sbc);
+            gy[k] = hsub2(A[k], sh);
+            sab[k] = sbc;
+            dhb[k] = dh;
+            A[k] = sh;
         }
-        if (++s == S) { s = 0; ph ^= 1; }
+        if (emit && mode) {
+            const uint4 o = sobel_mag16(gx, gy, half);
+            uint8_t *q = out - dpitch;
+            if (mode == 1) *reinterpret_cast<uint4 *>(q) = o;
+            else store_edge16(q, o, mode, plast);
+        }
+        out += dpitch;
+        so += stage_bytes;
+        fb += 8;
+        if (so == ring_bytes) { so = 0; fb = fb0; ph ^= 1; }
+      }
     }
 }
 
@@ -223,7 +282,7 @@ __global__ void __launch_bounds__(256) sobel_generic_kernel(const StencilArgs a)
     }
 }
 
-template <int CH, int FMA_MODE>
+template <int CH, int FMA_MODE, bool BIAS>
 static cudaError_t launch_sobel_t(const StencilArgs &a, int sm_count, cudaStream_t st) {
     if (a.width < 3 || a.nframes < 1) return cudaSuccess;
     const int out_rows = a.height - (a.halo_above ? 0 : 1) - (a.halo_below ? 0 : 1);
@@ -249,9 +308,9 @@ static cudaError_t launch_sobel_t(const StencilArgs &a, int sm_count, cudaStream
     p.stage_bytes = (uint32_t)((32 + p.nw * 512 * CH + 127) & ~127);
     // occupancy target: ~24-32 resident warps per SM
     const int occ = max(1, min(4, 30 / (p.nw + 1)));
-    const int budget = (227 * 1024) / occ - 1024 - 512;
+    const int budget = (227 * 1024) / occ - 1024 - 768;
     p.stages = max(3, min(12, budget / (int)p.stage_bytes));
-    const int smem = p.stages * (int)p.stage_bytes + 16 * p.stages + 2 * p.nw * 8 + 64;
+    const int smem = p.stages * (int)p.stage_bytes + 16 * p.stages + 2 * p.nw * 8 + 256 + 64;
     // bands: ~128 rows when there is plenty of work, fewer rows (>=16) when the launch is small
     const long long want_ctas = (long long)sm_count * occ * 4;
     int rpb = 128;
@@ -265,22 +324,30 @@ static cudaError_t launch_sobel_t(const StencilArgs &a, int sm_count, cudaStream
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (!(attr_mask >> dev & 1ULL)) {
-        e = cudaFuncSetAttribute(sobel_rows_kernel<CH, FMA_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        e = cudaFuncSetAttribute(sobel_rows_kernel<CH, FMA_MODE, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_mask |= 1ULL << dev;
     }
     const long long gx = (long long)a.nframes * p.nbands;
     if (gx > 0x7fffffffLL || nstrips > 65535) return cudaErrorInvalidValue;
     count_launch();
-    sobel_rows_kernel<CH, FMA_MODE><<<dim3((unsigned)gx, (unsigned)nstrips), (p.nw + 1) * 32, smem, st>>>(p);
+    sobel_rows_kernel<CH, FMA_MODE, BIAS><<<dim3((unsigned)gx, (unsigned)nstrips), (p.nw + 1) * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_sobel(const StencilArgs &a, int sm_count, cudaStream_t st) {
+    if (a.no_bias) {
+        switch (a.channels) {
+            case 1: return launch_sobel_t<1, 0, false>(a, sm_count, st);
+            case 3: return a.fma_mode ? launch_sobel_t<3, 1, false>(a, sm_count, st) : launch_sobel_t<3, 0, false>(a, sm_count, st);
+            case 4: return a.fma_mode ? launch_sobel_t<4, 1, false>(a, sm_count, st) : launch_sobel_t<4, 0, false>(a, sm_count, st);
+        }
+        return cudaErrorInvalidValue;
+    }
     switch (a.channels) {
-        case 1: return launch_sobel_t<1, 0>(a, sm_count, st);
-        case 3: return a.fma_mode ? launch_sobel_t<3, 1>(a, sm_count, st) : launch_sobel_t<3, 0>(a, sm_count, st);
-        case 4: return a.fma_mode ? launch_sobel_t<4, 1>(a, sm_count, st) : launch_sobel_t<4, 0>(a, sm_count, st);
+        case 1: return launch_sobel_t<1, 0, true>(a, sm_count, st);
+        case 3: return a.fma_mode ? launch_sobel_t<3, 1, true>(a, sm_count, st) : launch_sobel_t<3, 0, true>(a, sm_count, st);
+        case 4: return a.fma_mode ? launch_sobel_t<4, 1, true>(a, sm_count, st) : launch_sobel_t<4, 0, true>(a, sm_count, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -289,13 +356,13 @@ cudaError_t launch_sobel(const StencilArgs &a, int sm_count, cudaStream_t st) {
 // self tests of the magnitude path
 // ---------------------------------------------------------------------------------------------
 // out[m] = sat_u8(trunc(sqrt.approx(m + 0.5)))  -- must equal min(255, isqrt(m)) for every m
-__global__ void isqrt_selftest_kernel(uint8_t *out, unsigned int count) {
+__global__ void isqrt_selftest_kernel(uint8_t *out, unsigned int count, float bias) {
     for (unsigned int m = blockIdx.x * blockDim.x + threadIdx.x; m < count; m += gridDim.x * blockDim.x)
-        out[m] = (uint8_t)(pack_sat_u8(0.f, sqrt_approx((float)m + 0.5f), 0u) & 255u);
+        out[m] = (uint8_t)(pack_sat_u8(0.f, sqrt_approx((float)m + bias), 0u) & 255u);
 }
-cudaError_t launch_isqrt_selftest(uint8_t *out_dev, unsigned int count, cudaStream_t st) {
+cudaError_t launch_isqrt_selftest(uint8_t *out_dev, unsigned int count, float bias, cudaStream_t st) {
     count_launch();
-    isqrt_selftest_kernel<<<1024, 256, 0, st>>>(out_dev, count);
+    isqrt_selftest_kernel<<<1024, 256, 0, st>>>(out_dev, count, bias);
     return cudaGetLastError();
 }
 

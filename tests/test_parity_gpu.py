@@ -52,7 +52,34 @@ def test_isqrt_path_exhaustive(gpu):
     r = np.floor(np.sqrt(m.astype(np.float64))).astype(np.int64)
     r = np.where(r * r > m, r - 1, r)
     r = np.where((r + 1) * (r + 1) <= m, r + 1, r)
-    assert np.array_equal(got, np.minimum(r, 255).astype(np.uint8))
+    want = np.minimum(r, 255).astype(np.uint8)
+    assert np.array_equal(got, want)
+    # without the +0.5 guard the result depends on the MUFU.SQRT unit; the library checks this same table at
+    # init and only then drops the guard
+    exact = gpu.lib().ompimg_sqrt_is_exact()
+    assert exact in (0, 1)
+    assert bool(exact) == bool(np.array_equal(gpu.isqrt_table(n, 0.0), want))
+
+
+def test_sobel_with_the_sqrt_guard_forced(O):
+    """OMPIMG_SQRT_GUARD=1 keeps the +0.5 guard kernels: same bits."""
+    import os, subprocess, sys
+    code = r'''
+import importlib, sys, numpy as np
+sys.path.insert(0, "oracle"); import oracle as O
+pkg = importlib.import_module("openmp-parallel-computing_b200"); pkg.init(0)
+assert pkg.lib().ompimg_sqrt_is_exact() == 0
+rgb = O.synth(270 * 1000 * 3, 77).reshape(270, 1000, 3)
+assert np.array_equal(pkg.gray_sobel_pass(rgb.copy())[0], O.gray_sobel_pass(rgb.copy())[0])
+plane = O.synth(300 * 2000, 78).reshape(300, 2000)
+step = np.zeros((64, 1024), np.uint8); step[:, 500:] = 200; step[30:, :] += 55
+for p in (plane, step):
+    assert np.array_equal(pkg.sobel_edge(p), O.sobel(p))
+print("guard ok")
+'''
+    from common import ROOT
+    r = subprocess.run([sys.executable, "-c", code], cwd=str(ROOT), env=dict(os.environ, OMPIMG_SQRT_GUARD="1"), capture_output=True, text=True)
+    assert r.returncode == 0 and "guard ok" in r.stdout, r.stderr[-2000:]
 
 
 def test_synth_matches_oracle(gpu, O):
