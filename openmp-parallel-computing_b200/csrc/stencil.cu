@@ -17,7 +17,7 @@
 
 namespace ompimg {
 
-constexpr int ST_MAX_NW = 8;
+constexpr int ST_MAX_NW = 8;      // consumer warps per CTA
 
 struct StencilParams {
     const uint8_t *src;
@@ -42,7 +42,7 @@ __device__ __forceinline__ void load_group_words(uint32_t addr, uint32_t (&w)[4 
 }
 
 template <int CH, int FMA_MODE, bool BIAS>
-__global__ void __launch_bounds__((ST_MAX_NW + 1) * 32) sobel_rows_kernel(const StencilParams p) {
+__global__ void __launch_bounds__((ST_MAX_NW + 1) * 32, CH == 1 ? 3 : 2) sobel_rows_kernel(const StencilParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int BPP = CH;                      // bytes per source pixel
     const int NW = p.nw, S = p.stages;
@@ -58,7 +58,9 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32) sobel_rows_kernel(const 
     const uint8_t *src = p.src + (size_t)frame * p.src_stride;
     uint8_t *dst = p.dst + (size_t)frame * p.dst_stride;
 
-    const int ya = band * p.rows_per_band, yb = min(p.height, ya + p.rows_per_band);
+    // band 0 takes rows_per_band+1 output rows, every other band rows_per_band: with rows_per_band = 2 (mod 4)
+    // each band then consumes a multiple of four source rows (the row loop below runs four rows per trip)
+    const int ya = band == 0 ? 0 : band * p.rows_per_band + 1, yb = min(p.height, (band + 1) * p.rows_per_band + 1);
     const int rin0 = max(ya - 1, p.halo_above ? -1 : 0);
     const int rin1 = min(yb, p.halo_below ? p.height : p.height - 1);
     const int nin = rin1 - rin0 + 1;              // source rows this CTA consumes; outputs rows rin0+1 .. rin1-1
@@ -78,8 +80,8 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32) sobel_rows_kernel(const 
         const uint32_t dst_off = xs == 0 ? 16u : 0u;
         int s = 0;
         uint32_t ph = 0;
-        const int nin_even = (nin + 1) & ~1;      // consumers take rows two at a time
-        for (int i = 0; i < nin_even; ++i) {
+        const int nin_pad = (nin + 3) & ~3;       // consumers take rows four at a time
+        for (int i = 0; i < nin_pad; ++i) {
             const int r = min(rin0 + i, rin1);
             if (i >= S) mbar_wait(empty0 + 8 * s, ph ^ 1);
             const uint32_t d = smem0 + s * p.stage_bytes + dst_off;
@@ -155,14 +157,17 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32) sobel_rows_kernel(const 
     uint32_t fb = fb0;               // its full barrier (the empty barrier sits 8*S bytes above)
     uint32_t ph = 0;
 
-    // Rows are consumed two per trip so that the roles of the two Sh' register sets alternate
-    // without copies: A holds Sh' of the oldest row on entry and of the newest row on exit.
-    // (an odd row count is padded with one dummy row whose result is not stored; the producer
-    // re-sends the last row for it)
-    for (int i = 0; i < nin; i += 2) {
+    // Rows are consumed four per trip: the two Sh' register sets alternate roles every row (A holds
+    // Sh' of the oldest row on entry and of the newest row on exit).  A row count that is not a
+    // multiple of four is padded with dummy rows whose results are not stored (the producer
+    // re-sends the last row for them).
+    // (Fetching the next row's words before the sqrt/pack/store tail was tried and measured slower:
+    // the extra live registers cost more than the exposed shared-memory latency.)
+    for (int i = 0; i < nin; i += 4) {
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const bool emit = i >= 2 && (hh == 0 || i + 1 < nin);   // the first two rows only prime the row state
+      for (int r4 = 0; r4 < 4; ++r4) {
+        const int hh = r4 & 1;
+        const bool emit = i + r4 >= 2 && i + r4 < nin;          // the first two rows only prime the row state
         uint32_t (&A)[8] = hh ? shY : shX;
         const uint32_t stage = my + so;
         mbar_wait(fb, ph);
@@ -313,11 +318,10 @@ static cudaError_t launch_sobel_t(const StencilArgs &a, int sm_count, cudaStream
     const int smem = p.stages * (int)p.stage_bytes + 16 * p.stages + 2 * p.nw * 8 + 256 + 64;
     // bands: ~128 rows when there is plenty of work, fewer rows (>=16) when the launch is small
     const long long want_ctas = (long long)sm_count * occ * 4;
-    int rpb = 128;
-    while (rpb > 16 && (long long)a.nframes * nstrips * ((a.height + rpb - 1) / rpb) < want_ctas) rpb /= 2;
-    if (rpb > a.height) rpb = a.height;
+    int rpb = 130;                                    // 2 (mod 4), see the kernel
+    while (rpb > 18 && (long long)a.nframes * nstrips * ((a.height - 1 + rpb - 1) / rpb) < want_ctas) rpb = (rpb - 2) / 2 + 2;   // 130, 66, 34, 18
     p.rows_per_band = rpb;
-    p.nbands = (a.height + rpb - 1) / rpb;
+    p.nbands = max(1, (a.height - 1 + rpb - 1) / rpb);
 
     static unsigned long long attr_mask = 0;
     int dev = 0;
