@@ -425,3 +425,37 @@ def test_full_size_convolution_box_property(gpu, O):
         got = np.stack([out.download(ww * 3, offset=((y0 + r) * cols + x0) * 3) for r in range(hh)]).reshape(hh, ww, 3)
         assert np.array_equal(got, want)
         src.free(); out.free()
+
+
+# ------------------------------------------------------------------------------------------------ drop-in CLI
+def _run_cli(binary, image, passes, tmp_path, env_extra=None):
+    import hashlib, os, subprocess
+    from common import ROOT
+    exe = ROOT / "oracle" / "_ref" / "bin" / binary
+    img = ROOT / "oracle" / "_ref" / "fixtures" / image
+    if not exe.exists() or not img.exists():
+        pytest.skip("drop-in binaries not built (oracle/Makefile `dropin`, needs /root/reference at build time)")
+    out = tmp_path / f"{binary}_{passes}.png"
+    r = subprocess.run([str(exe), str(img), str(out), str(passes)], capture_output=True, text=True, env=dict(os.environ, **(env_extra or {})))
+    assert r.returncode == 0, r.stderr
+    return hashlib.md5(out.read_bytes()).hexdigest(), r.stdout
+
+
+def test_reference_main_c_linked_against_the_library(gpu, golden, tmp_path):
+    """BASELINE config 1: the reference's unmodified main.c, linked with libompimg_b200 instead of its own
+    parallel_to_grayscale.c, writes a PNG byte-identical to the reference's golden images/test_gray.png."""
+    md5, out = _run_cli("grayscale_b200", "test.jpg", 1, tmp_path)
+    assert md5 == golden["test_jpg"]["golden_png_md5"] == "044e265e3fd33938ff9a655156297af6"
+    assert "Compute kernel" in out                                  # main.c:39, the line the workers' scripts show
+    assert _run_cli("grayscale_b200", "test.jpg", 3, tmp_path)[0] == golden["test_jpg"]["strict_p3_png_md5"]
+    assert _run_cli("grayscale_b200", "test.jpg", 1, tmp_path, {"OMPIMG_LUMA": "fma"})[0] == golden["test_jpg"]["native_p1_png_md5"]
+    # OMP_NUM_THREADS is what the reference's callers vary (1/2/4/6); the GPU library ignores it: same bytes
+    for t in ("1", "6"):
+        assert _run_cli("grayscale_b200", "test.jpg", 1, tmp_path, {"OMP_NUM_THREADS": t})[0] == golden["test_jpg"]["golden_png_md5"]
+
+
+def test_reference_main_with_sobel_c_linked_against_the_library(gpu, golden, tmp_path):
+    """BASELINE config 2: main_with_sobel.c (gray -> extract -> Sobel -> replicate) with both kernels on the GPU."""
+    assert _run_cli("sobel_b200", "more_than_one_mega_photo.jpg", 1, tmp_path)[0] == golden["photo_jpg"]["strict_p1_png_md5"]
+    assert _run_cli("sobel_b200", "more_than_one_mega_photo.jpg", 2, tmp_path)[0] == golden["photo_jpg"]["strict_p2_png_md5"]
+    assert _run_cli("sobel_b200", "more_than_one_mega_photo.jpg", 1, tmp_path, {"OMPIMG_LUMA": "fma"})[0] == golden["photo_jpg"]["native_p1_png_md5"]
