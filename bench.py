@@ -37,6 +37,17 @@ BYTES_PER_PX = 4.0          # algorithmic: 3 B RGB read + 1 B edge written (SURV
 SEED = 0xB2000003
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def shard(total: int, rank: int, world: int):
     """contiguous block of frames for `rank`: no frame is split, none is shared"""
     lo = total * rank // world
@@ -230,7 +241,7 @@ def run_reference(args, dist: Dist):
         "e2e": {"value": value, "unit": "Gpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -328,7 +339,7 @@ def run_ours(args, dist: Dist):
         }
         if extras:
             line["other_kernels"] = extras
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 def other_kernels(pkg, L, peak):
@@ -411,6 +422,11 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--backend", default="nccl")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) go to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     dist = Dist("gloo" if args.impl == "reference" else args.backend)
     try:
         if args.impl == "reference":

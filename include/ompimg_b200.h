@@ -74,6 +74,7 @@ OMPIMG_API void *ompimg_dev_alloc(size_t bytes);           /* cudaMalloc, NULL o
 OMPIMG_API int   ompimg_dev_free(void *p);
 OMPIMG_API void *ompimg_host_alloc(size_t bytes);          /* pinned host memory */
 OMPIMG_API int   ompimg_host_free(void *p);
+OMPIMG_API void *ompimg_host_realloc_sized(void *p, size_t old_bytes, size_t new_bytes);   /* for STBI_REALLOC_SIZED (stb_image.h:673-684) */
 OMPIMG_API int   ompimg_host_register(void *p, size_t bytes);   /* pin caller-owned pageable memory */
 OMPIMG_API int   ompimg_host_unregister(void *p);
 OMPIMG_API int   ompimg_memset_dev(void *dst, int value, size_t bytes, int stream);

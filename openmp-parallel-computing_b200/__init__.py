@@ -67,6 +67,7 @@ _SIGS = {
     "ompimg_dev_free": (C.c_int, [_vp]),
     "ompimg_host_alloc": (_vp, [_sz]),
     "ompimg_host_free": (C.c_int, [_vp]),
+    "ompimg_host_realloc_sized": (_vp, [_vp, _sz, _sz]),
     "ompimg_host_register": (C.c_int, [_vp, _sz]),
     "ompimg_host_unregister": (C.c_int, [_vp]),
     "ompimg_memset_dev": (C.c_int, [_vp, C.c_int, _sz, C.c_int]),

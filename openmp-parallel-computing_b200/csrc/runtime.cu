@@ -226,6 +226,14 @@ extern "C" void *ompimg_host_alloc(size_t bytes) {
     return p;
 }
 extern "C" int ompimg_host_free(void *p) { INIT(); CK(cudaFreeHost(p)); return OMPIMG_OK; }
+extern "C" void *ompimg_host_realloc_sized(void *p, size_t old_bytes, size_t new_bytes) {
+    void *q = ompimg_host_alloc(new_bytes);
+    if (q && p) {
+        memcpy(q, p, old_bytes < new_bytes ? old_bytes : new_bytes);
+        cudaFreeHost(p);
+    }
+    return q;
+}
 extern "C" int ompimg_host_register(void *p, size_t bytes) { INIT(); CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable)); return OMPIMG_OK; }
 extern "C" int ompimg_host_unregister(void *p) { INIT(); CK(cudaHostUnregister(p)); return OMPIMG_OK; }
 extern "C" int ompimg_memset_dev(void *dst, int value, size_t bytes, int stream) {
