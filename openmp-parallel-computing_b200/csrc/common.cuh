@@ -209,6 +209,25 @@ __device__ __forceinline__ uint32_t luma1(uint32_t r, uint32_t g, uint32_t b) {
     return (uint32_t)(int)v;   // v in [0,255]: truncation toward zero
 }
 
+// one pixel whose r,g,b are bytes 0..2 of `px` -> fp32 bit pattern (MAGIC + luma); same arithmetic as luma2
+template <int FMA_MODE>
+__device__ __forceinline__ uint32_t luma_px(uint32_t px, float magic) {
+    const uint32_t Z = 0x4B000000u;
+    const float xr = __uint_as_float(prmt(px, Z, 0x7440)), xg = __uint_as_float(prmt(px, Z, 0x7441)), xb = __uint_as_float(prmt(px, Z, 0x7442));
+    float v;
+    if (FMA_MODE == 0) {
+        const float pr = __fmaf_rn(OMPIMG_KR, xr, -OMPIMG_KR * OMPIMG_TWO23);
+        const float pg = __fmaf_rn(OMPIMG_KG, xg, -OMPIMG_KG * OMPIMG_TWO23);
+        const float pb = __fmaf_rn(OMPIMG_KB, xb, -OMPIMG_KB * OMPIMG_TWO23);
+        v = __fadd_rn(__fadd_rn(pr, pg), pb);
+    } else {
+        const float pg = __fmaf_rn(OMPIMG_KG, xg, -OMPIMG_KG * OMPIMG_TWO23);
+        const float t = __fmaf_rn(OMPIMG_KR, __fadd_rn(xr, -OMPIMG_TWO23), pg);
+        v = __fmaf_rn(OMPIMG_KB, __fadd_rn(xb, -OMPIMG_TWO23), t);
+    }
+    return __float_as_uint(__fadd_rz(v, magic));
+}
+
 // 16 pixels of interleaved RGB (12 words) -> 16 fp32 bit patterns (MAGIC + luma)
 template <int FMA_MODE>
 __device__ __forceinline__ void luma16_rgb(const uint32_t (&w)[12], uint32_t (&f)[16], float magic) {

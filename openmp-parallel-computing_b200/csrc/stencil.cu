@@ -48,9 +48,8 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32, CH == 1 ? 3 : 2) sobel_r
     const int NW = p.nw, S = p.stages;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem0 = smem_u32(smem);
-    const uint32_t full0 = smem0 + S * p.stage_bytes;     // S full barriers, S empty barriers, edge exchange
+    const uint32_t full0 = smem0 + S * p.stage_bytes;     // S full barriers, then S empty barriers
     const uint32_t empty0 = full0 + 8 * S;
-    const uint32_t edge0 = empty0 + 8 * S;                // [2][NW][2] words
 
     const int frame = blockIdx.x / p.nbands, band = blockIdx.x - frame * p.nbands;
     const int SW = NW * 512;
@@ -126,24 +125,14 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32, CH == 1 ? 3 : 2) sobel_r
     const uint32_t eoff = keep(8u * (uint32_t)S);
     const uint32_t fb0 = keep(full0);
     const uint32_t lane0 = keep(lane == 0 ? 1u : 0u);
-    const uint32_t ncons = keep((uint32_t)NW * 32u);
-    const bool multi_strip = gridDim.y > 1;
-    // warp-edge luma exchange: lane 0 publishes its first luma, lane 31 its last one, every other lane
-    // writes to a scratch word; lane 0 / 31 of an inner warp read the neighbour warp's value, selected
-    // with a mask instead of a branch
-    const uint32_t dummy0 = edge0 + 2u * (uint32_t)NW * 8u;
-    const uint32_t ex_par = (uint32_t)NW * 8u;
-    const uint32_t exw = edge0 + (uint32_t)warp * 8u;
-    uint32_t stsA[2], stsB[2], ldsL[2], ldsR[2];
-#pragma unroll
-    for (int par = 0; par < 2; ++par) {
-        stsA[par] = keep(lane == 0 ? exw + par * ex_par : dummy0 + 4u * lane);
-        stsB[par] = keep(lane == 31 ? exw + par * ex_par + 4u : dummy0 + 128u + 4u * lane);
-        ldsL[par] = keep(exw + par * ex_par - 4u);
-        ldsR[par] = keep(exw + par * ex_par + 8u);
-    }
-    const uint32_t mL = keep((lane == 0 && warp > 0) ? 0xffffffffu : 0u);
-    const uint32_t mR = keep((lane == 31 && warp < NW - 1) ? 0xffffffffu : 0u);
+    // warp-edge lumas of the fused path: lane 0 needs the luma of the pixel left of its group, lane 31 of the
+    // pixel right of its group.  Both pixels are in the stage (neighbour warp's bytes, or the 16-byte
+    // halo blocks at the strip ends), so every warp recomputes its own two edge lumas: one extra pixel
+    // of luma arithmetic per row instead of a CTA-wide barrier, and the warps stay independent.
+    const int edge_off = lane == 0 ? -4 : 16 * BPP;                         // word that holds the edge pixel
+    const uint32_t edge_sh = keep(lane == 0 ? 8u * (4u - BPP) : 0u);         // its bytes start here
+    const uint32_t mL = keep(lane == 0 ? 0xffffffffu : 0u);
+    const uint32_t mR = keep(lane == 31 ? 0xffffffffu : 0u);
     const size_t dpitch = keep64(p.dst_pitch);
     uint8_t *out = dst + (size_t)rin0 * p.dst_pitch + x0;     // row of the stage being consumed; stores go one row up
     float half = BIAS ? 0.5f : 0.0f;
@@ -192,29 +181,18 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32, CH == 1 ? 3 : 2) sobel_r
         } else {
             uint32_t w[4 * CH];
             load_group_words<CH>(stage, w);
-            uint32_t eL = 0, eR = 0;
-            if (multi_strip) {       // strip-edge pixels xs-1 and xs+SW (images wider than one strip only)
-                eL = lds32(smem0 + so + 12) >> (8 * (4 - BPP));
-                eR = lds32(smem0 + so + 16 + (uint32_t)SW * BPP);
-            }
+            const uint32_t ew = lds32(stage + edge_off) >> edge_sh;          // r,g,b of the edge pixel in bytes 0..2
             __syncwarp();
             if (lane0) mbar_arrive(fb + eoff);
             uint32_t f[16];
             const float MAGIC = 14942208.0f;      // 2^23 + 0x640000: result bits 0x4B6400ll
             if (CH == 3) luma16_rgb<FMA_MODE>(reinterpret_cast<const uint32_t(&)[12]>(w), f, MAGIC);
             else luma16_rgba<FMA_MODE>(reinterpret_cast<const uint32_t(&)[16]>(w), f, MAGIC);
-            sts32(stsA[hh], f[0]);
-            sts32(stsB[hh], f[15]);
-            named_bar_sync(1, ncons);
+            const uint32_t fE = luma_px<FMA_MODE>(ew, MAGIC);
             uint32_t fL = __shfl_up_sync(0xffffffffu, f[15], 1);
             uint32_t fR = __shfl_down_sync(0xffffffffu, f[0], 1);
-            const uint32_t nL = lds32(ldsL[hh]), nR = lds32(ldsR[hh]);
-            fL = (nL & mL) | (fL & ~mL);
-            fR = (nR & mR) | (fR & ~mR);
-            if (multi_strip) {
-                if (warp == 0 && lane == 0 && xs > 0) fL = 0x4B640000u | luma1<FMA_MODE>(eL & 255u, (eL >> 8) & 255u, (eL >> 16) & 255u);
-                if (warp == NW - 1 && lane == 31 && xs + SW < p.width) fR = 0x4B640000u | luma1<FMA_MODE>(eR & 255u, (eR >> 8) & 255u, (eR >> 16) & 255u);
-            }
+            fL = (fE & mL) | (fL & ~mL);
+            fR = (fE & mR) | (fR & ~mR);
 #pragma unroll
             for (int k = 0; k < 8; ++k) P[k] = prmt(f[2 * k], f[2 * k + 1], 0x6420);
             Q[0] = prmt(fL, f[0], 0x6420);
@@ -315,7 +293,7 @@ static cudaError_t launch_sobel_t(const StencilArgs &a, int sm_count, cudaStream
     const int occ = max(1, min(4, 30 / (p.nw + 1)));
     const int budget = (227 * 1024) / occ - 1024 - 768;
     p.stages = max(3, min(12, budget / (int)p.stage_bytes));
-    const int smem = p.stages * (int)p.stage_bytes + 16 * p.stages + 2 * p.nw * 8 + 256 + 64;
+    const int smem = p.stages * (int)p.stage_bytes + 16 * p.stages + 64;
     // bands: ~128 rows when there is plenty of work, fewer rows (>=16) when the launch is small
     const long long want_ctas = (long long)sm_count * occ * 4;
     int rpb = 130;                                    // 2 (mod 4), see the kernel
