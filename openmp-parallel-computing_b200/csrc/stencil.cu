@@ -57,8 +57,8 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32, CH == 1 ? 3 : 2) sobel_r
     const uint8_t *src = p.src + (size_t)frame * p.src_stride;
     uint8_t *dst = p.dst + (size_t)frame * p.dst_stride;
 
-    // band 0 takes rows_per_band+1 output rows, every other band rows_per_band: with rows_per_band = 2 (mod 4)
-    // each band then consumes a multiple of four source rows (the row loop below runs four rows per trip)
+    // band 0 takes rows_per_band+1 output rows, every other band rows_per_band: with rows_per_band = 1 (mod 3)
+    // each band then consumes a multiple of three source rows (the row loop below runs three rows per trip)
     const int ya = band == 0 ? 0 : band * p.rows_per_band + 1, yb = min(p.height, (band + 1) * p.rows_per_band + 1);
     const int rin0 = max(ya - 1, p.halo_above ? -1 : 0);
     const int rin1 = min(yb, p.halo_below ? p.height : p.height - 1);
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32, CH == 1 ? 3 : 2) sobel_r
         const uint32_t dst_off = xs == 0 ? 16u : 0u;
         int s = 0;
         uint32_t ph = 0;
-        const int nin_pad = (nin + 3) & ~3;       // consumers take rows four at a time
+        const int nin_pad = (nin + 2) / 3 * 3;    // consumers take rows three at a time
         for (int i = 0; i < nin_pad; ++i) {
             const int r = min(rin0 + i, rin1);
             if (i >= S) mbar_wait(empty0 + 8 * s, ph ^ 1);
@@ -138,26 +138,30 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32, CH == 1 ? 3 : 2) sobel_r
     float half = BIAS ? 0.5f : 0.0f;
     if (BIAS) asm volatile("" : "+f"(half));
 
-    uint32_t sab[8], dhb[8], shX[8], shY[8];
+    // row state per pixel pair, in two three-register rotations (see the row loop)
+    uint32_t U[3][8], V[3][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) sab[k] = dhb[k] = shX[k] = shY[k] = 0u;
+    for (int k = 0; k < 8; ++k) U[0][k] = U[1][k] = U[2][k] = V[0][k] = V[1][k] = V[2][k] = 0u;
 
     uint32_t so = 0;                 // byte offset of the current stage in the ring
     uint32_t fb = fb0;               // its full barrier (the empty barrier sits 8*S bytes above)
     uint32_t ph = 0;
 
-    // Rows are consumed four per trip: the two Sh' register sets alternate roles every row (A holds
-    // Sh' of the oldest row on entry and of the newest row on exit).  A row count that is not a
-    // multiple of four is padded with dummy rows whose results are not stored (the producer
-    // re-sends the last row for them).
+    // Rows are consumed three per trip.  Per pixel pair the vertical recurrences rotate through three
+    // registers each, so that every update is in place and the register roles are back where they
+    // started after three rows (no copies at the loop back-edge):
+    //   U[a] = Dh(r-2)+Dh(r-1), U[b] = Dh(r-1), U[c] free:  U[c] = Dh(r); U[b] += U[c]; gx = U[a]+U[b];  then a,b,c <- b,c,a
+    //   V[a] = Sh'(r-2), V[b] = Sh'(r-1), V[c] free:        V[c] = Sh'(r); gy = V[a]-V[c];               then a,b,c <- b,c,a
+    // A row count that is not a multiple of three is padded with dummy rows whose results are not
+    // stored (the producer re-sends the last row for them).
     // (Fetching the next row's words before the sqrt/pack/store tail was tried and measured slower:
     // the extra live registers cost more than the exposed shared-memory latency.)
-    for (int i = 0; i < nin; i += 4) {
+    for (int i = 0; i < nin; i += 3) {
 #pragma unroll
-      for (int r4 = 0; r4 < 4; ++r4) {
-        const int hh = r4 & 1;
-        const bool emit = i + r4 >= 2 && i + r4 < nin;          // the first two rows only prime the row state
-        uint32_t (&A)[8] = hh ? shY : shX;
+      for (int rho = 0; rho < 3; ++rho) {
+        constexpr int dummy_ = 0; (void)dummy_;
+        const int ra = rho, rb = (rho + 1) % 3, rc = (rho + 2) % 3;
+        const bool emit = i + rho >= 2 && i + rho < nin;        // the first two rows only prime the row state
         const uint32_t stage = my + so;
         mbar_wait(fb, ph);
         uint32_t P[8], Q[9];
@@ -203,15 +207,12 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32, CH == 1 ? 3 : 2) sobel_r
         uint32_t gx[8], gy[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const uint32_t dh = hsub2(Q[k + 1], Q[k]);
+            U[rc][k] = hsub2(Q[k + 1], Q[k]);
             const uint32_t t1 = hfma2(P[k], 0x40004000u /*2,2*/, 0xEA00EA00u /*-3072,-3072*/);
-            const uint32_t sh = hadd2(hadd2(t1, Q[k]), Q[k + 1]);
-            const uint32_t sbc = hadd2(dhb[k], dh);
-            gx[k] = hadd2(sab[k], sbc);
-            gy[k] = hsub2(A[k], sh);
-            sab[k] = sbc;
-            dhb[k] = dh;
-            A[k] = sh;
+            V[rc][k] = hadd2(hadd2(t1, Q[k]), Q[k + 1]);
+            U[rb][k] = hadd2(U[rb][k], U[rc][k]);
+            gx[k] = hadd2(U[ra][k], U[rb][k]);
+            gy[k] = hsub2(V[ra][k], V[rc][k]);
         }
         if (emit && mode) {
             const uint4 o = sobel_mag16(gx, gy, half);
@@ -296,8 +297,8 @@ static cudaError_t launch_sobel_t(const StencilArgs &a, int sm_count, cudaStream
     const int smem = p.stages * (int)p.stage_bytes + 16 * p.stages + 64;
     // bands: ~128 rows when there is plenty of work, fewer rows (>=16) when the launch is small
     const long long want_ctas = (long long)sm_count * occ * 4;
-    int rpb = 130;                                    // 2 (mod 4), see the kernel
-    while (rpb > 18 && (long long)a.nframes * nstrips * ((a.height - 1 + rpb - 1) / rpb) < want_ctas) rpb = (rpb - 2) / 2 + 2;   // 130, 66, 34, 18
+    int rpb = 130;                                    // 1 (mod 3), see the kernel
+    while (rpb > 16 && (long long)a.nframes * nstrips * ((a.height - 1 + rpb - 1) / rpb) < want_ctas) rpb = rpb == 130 ? 64 : rpb == 64 ? 34 : 16;
     p.rows_per_band = rpb;
     p.nbands = max(1, (a.height - 1 + rpb - 1) / rpb);
 
