@@ -125,6 +125,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) { }
 }
+// for a thread that is usually far ahead of the event it waits for (a producer waiting for a free stage):
+// sleep between probes instead of competing for issue slots with the warps doing the work
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(256);
+}
 // global -> shared, completion counted in bytes on `bar`.  src, dst 16-byte aligned, bytes % 16 == 0.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -28,7 +28,8 @@ struct StencilParams {
     int nbands, rows_per_band;
     int nw;             // consumer warps
     int stages;
-    uint32_t stage_bytes;
+    uint32_t stage_bytes;   // three row slots
+    uint32_t row_slot;      // bytes reserved per row in a stage (16-byte halo blocks included)
     uint32_t row_bytes16;   // round16(width*bpp)
 };
 
@@ -79,25 +80,30 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32, CH == 1 ? 3 : 2) sobel_r
         const uint32_t dst_off = xs == 0 ? 16u : 0u;
         int s = 0;
         uint32_t ph = 0;
-        const int nin_pad = (nin + 2) / 3 * 3;    // consumers take rows three at a time
-        for (int i = 0; i < nin_pad; ++i) {
-            const int r = min(rin0 + i, rin1);
-            if (i >= S) mbar_wait(empty0 + 8 * s, ph ^ 1);
-            const uint32_t d = smem0 + s * p.stage_bytes + dst_off;
-            if (r >= 0 && r < p.height) {
-                if (lane == 0) {
-                    mbar_expect_tx(full0 + 8 * s, bytes);
-                    bulk_g2s(d, src + (size_t)r * p.src_pitch + lo, bytes, full0 + 8 * s);
+        const int ntrips = (nin + 2) / 3;         // a stage holds three consecutive rows: one wait / one release per trip
+        for (int t = 0; t < ntrips; ++t) {
+            if (t >= S) mbar_wait_relaxed(empty0 + 8 * s, ph ^ 1);
+            const uint32_t d0 = smem0 + s * p.stage_bytes + dst_off;
+            uint32_t tx = 0;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int r = min(rin0 + 3 * t + j, rin1);
+                if (r < 0 || r >= p.height) {
+                    // halo row owned by a neighbouring band (peer device memory over NVLink): plain loads
+                    const uint8_t *row = (r < 0 ? p.halo_above : p.halo_below) + lo;
+                    for (uint32_t q = lane * 16; q < bytes; q += 32 * 16) sts128(d0 + j * p.row_slot + q, *reinterpret_cast<const uint4 *>(row + q));
+                } else {
+                    tx += bytes;
                 }
-            } else {
-                // halo row owned by a neighbouring band (peer device memory over NVLink)
-                const uint8_t *row = (r < 0 ? p.halo_above : p.halo_below) + lo;
-                for (uint32_t j = lane * 16; j < bytes; j += 32 * 16) {
-                    const uint4 v = *reinterpret_cast<const uint4 *>(row + j);
-                    sts128(d + j, v);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_expect_tx(full0 + 8 * s, tx);             // also releases the stores above to the consumers
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int r = min(rin0 + 3 * t + j, rin1);
+                    if (r >= 0 && r < p.height) bulk_g2s(d0 + j * p.row_slot, src + (size_t)r * p.src_pitch + lo, bytes, full0 + 8 * s);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full0 + 8 * s);
             }
             if (++s == S) { s = 0; ph ^= 1; }
         }
@@ -121,6 +127,7 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32, CH == 1 ? 3 : 2) sobel_r
     const int plast = min(16, p.width - 1 - x0);  // valid bytes are [x0 == 0, plast)
     const uint32_t my = keep(smem0 + 16u + (uint32_t)c * (16u * BPP));
     const uint32_t stage_bytes = keep(p.stage_bytes);
+    const uint32_t row_slot = keep(p.row_slot);
     const uint32_t ring_bytes = keep((uint32_t)S * p.stage_bytes);
     const uint32_t eoff = keep(8u * (uint32_t)S);
     const uint32_t fb0 = keep(full0);
@@ -162,15 +169,15 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32, CH == 1 ? 3 : 2) sobel_r
         constexpr int dummy_ = 0; (void)dummy_;
         const int ra = rho, rb = (rho + 1) % 3, rc = (rho + 2) % 3;
         const bool emit = i + rho >= 2 && i + rho < nin;        // the first two rows only prime the row state
-        const uint32_t stage = my + so;
-        mbar_wait(fb, ph);
+        const uint32_t stage = my + so + (uint32_t)rho * row_slot;
+        if (rho == 0) mbar_wait(fb, ph);
         uint32_t P[8], Q[9];
         if (CH == 1) {
             const uint32_t C64 = 0x64646464u;
             const uint4 v = lds128(stage);
             const uint32_t lw = lds32(stage - 4), rw = lds32(stage + 16);
             __syncwarp();
-            if (lane0) mbar_arrive(fb + eoff);
+            if (rho == 2 && lane0) mbar_arrive(fb + eoff);   // all three rows of the stage are in registers / consumed
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -187,7 +194,7 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32, CH == 1 ? 3 : 2) sobel_r
             load_group_words<CH>(stage, w);
             const uint32_t ew = lds32(stage + edge_off) >> edge_sh;          // r,g,b of the edge pixel in bytes 0..2
             __syncwarp();
-            if (lane0) mbar_arrive(fb + eoff);
+            if (rho == 2 && lane0) mbar_arrive(fb + eoff);   // all three rows of the stage are in registers / consumed
             uint32_t f[16];
             const float MAGIC = 14942208.0f;      // 2^23 + 0x640000: result bits 0x4B6400ll
             if (CH == 3) luma16_rgb<FMA_MODE>(reinterpret_cast<const uint32_t(&)[12]>(w), f, MAGIC);
@@ -221,9 +228,11 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32, CH == 1 ? 3 : 2) sobel_r
             else store_edge16(q, o, mode, plast);
         }
         out += dpitch;
-        so += stage_bytes;
-        fb += 8;
-        if (so == ring_bytes) { so = 0; fb = fb0; ph ^= 1; }
+        if (rho == 2) {
+            so += stage_bytes;
+            fb += 8;
+            if (so == ring_bytes) { so = 0; fb = fb0; ph ^= 1; }
+        }
       }
     }
 }
@@ -289,11 +298,12 @@ static cudaError_t launch_sobel_t(const StencilArgs &a, int sm_count, cudaStream
     p.nw = min(ST_MAX_NW, (a.width + 511) / 512);
     const int nstrips = (a.width + p.nw * 512 - 1) / (p.nw * 512);
     p.row_bytes16 = (uint32_t)(((size_t)a.width * CH + 15) & ~(size_t)15);
-    p.stage_bytes = (uint32_t)((32 + p.nw * 512 * CH + 127) & ~127);
+    p.row_slot = (uint32_t)((32 + p.nw * 512 * CH + 127) & ~127);
+    p.stage_bytes = 3 * p.row_slot;
     // occupancy target: ~24-32 resident warps per SM
-    const int occ = max(1, min(4, 30 / (p.nw + 1)));
+    const int occ = CH == 1 ? max(1, min(4, 30 / (p.nw + 1))) : max(1, min(2, 30 / (p.nw + 1)));   // CTAs per SM the registers allow
     const int budget = (227 * 1024) / occ - 1024 - 768;
-    p.stages = max(3, min(12, budget / (int)p.stage_bytes));
+    p.stages = max(2, min(5, budget / (int)p.stage_bytes));
     const int smem = p.stages * (int)p.stage_bytes + 16 * p.stages + 64;
     // bands: ~128 rows when there is plenty of work, fewer rows (>=16) when the launch is small
     const long long want_ctas = (long long)sm_count * occ * 4;
