@@ -170,6 +170,8 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32, CH == 1 ? 3 : 2) sobel_r
         const int ra = rho, rb = (rho + 1) % 3, rc = (rho + 2) % 3;
         const bool emit = i + rho >= 2 && i + rho < nin;        // the first two rows only prime the row state
         const uint32_t stage = my + so + (uint32_t)rho * row_slot;
+        // (a warp that finds its stage not yet refilled is ahead of the slowest warp of the CTA -- the ring is only
+        // refilled when every warp has released a stage; sleeping there instead of re-probing measured the same)
         if (rho == 0) mbar_wait(fb, ph);
         uint32_t P[8], Q[9];
         if (CH == 1) {
