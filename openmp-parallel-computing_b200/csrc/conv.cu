@@ -86,6 +86,149 @@ __global__ void __launch_bounds__(256) conv_column_kernel(const ConvParams p, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast path: a thread owns FOUR adjacent output byte columns (one 32-bit word) and walks down a band.
+// Per input row it loads the M+1 aligned words that cover its window, builds the three byte-shifted
+// copies with PRMT, and forms the horizontal sums with dp4a against "dilated" tap words
+// (tap v[kc] sits at byte 3*kc, zeros elsewhere), i.e. four multiply-adds per instruction:
+//     h[b] = sum_m dp4a(bytes[b+4m .. b+4m+3], T[m])          b = 0..3
+// Separable taps (outer(u, v)): one such sum per row, then K multiply-adds into the K rotating
+// accumulators; generic taps: one sum per tap row.  Needs |taps| <= 127 (signed bytes), a 4-byte
+// aligned input and int32 accumulation; everything else takes conv_column_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int conv_m(int K) { return (3 * (K - 1) + 1 + 3) / 4; }     // dilated taps span 3(K-1)+1 bytes
+
+struct ConvWordTaps {
+    int32_t u[CONV_MAX_K];                        // separable: vertical taps
+    uint32_t t[9 * 7];                            // dilated tap words: separable T[m]; generic T[kr][m]
+};
+
+// d = c + sum_i (unsigned byte i of a) * (signed byte i of b)
+__device__ __forceinline__ int32_t dp4a_us(uint32_t a, uint32_t b, int32_t c) {
+    int32_t d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+template <int DIVMODE>
+__device__ __forceinline__ int32_t conv_div(int32_t acc, int32_t norm, uint32_t magic, int shift) {
+    if (DIVMODE == 0) return acc >> shift;                                   // taps >= 0, norm = 2^shift
+    if (DIVMODE == 1) return (int32_t)(__umulhi((uint32_t)acc, magic) >> shift);   // taps >= 0, norm > 0: exact for acc < 2^31
+    return acc / norm;                                                       // anything: C truncation toward zero
+}
+
+template <int K, bool SEPARABLE, int DIVMODE>
+__global__ void __launch_bounds__(256, K >= 7 ? 3 : 4) conv_word_kernel(const ConvParams p, const ConvWordTaps taps, uint32_t magic, int shift) {
+    constexpr int M = conv_m(K);
+    const int jw = blockIdx.x * blockDim.x + threadIdx.x;          // output word index in the row
+    const int nwords = (p.cols3 + 3) >> 2;
+    if (jw >= nwords) return;
+    const int r0 = blockIdx.y * p.band_rows, r1 = min(p.rows, r0 + p.band_rows);
+    // words past the end of the row only ever meet zero taps, but they must not be read past the
+    // allocation: the (few) threads whose window crosses the pitch re-read the row's last word instead
+    const int wmax = (int)(p.in_pitch >> 2) - 1;
+    int off[M + 1];
+#pragma unroll
+    for (int m = 0; m <= M; ++m) off[m] = min(jw + m, wmax) - jw;   // == m for every thread but the last ones of a row
+    int32_t acc[K][4];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[k][b] = 0;
+    const bool full = 4 * jw + 3 < p.cols3;
+    const bool inner = jw + M <= wmax;                               // warp-uniform except in the last warp of a row
+
+    // the words of the next input row are requested before the current row is processed (one row of
+    // software prefetch: the walk is otherwise exposed to the full memory latency once per row)
+    const uint32_t *rowp = reinterpret_cast<const uint32_t *>(p.in + (size_t)r0 * p.in_pitch) + jw;
+    const size_t pitch_w = p.in_pitch >> 2;
+    uint32_t wn[M + 1];
+    auto load_row = [&](const uint32_t *q) {
+        if (inner) {
+#pragma unroll
+            for (int m = 0; m <= M; ++m) wn[m] = __ldg(q + m);
+        } else {
+#pragma unroll
+            for (int m = 0; m <= M; ++m) wn[m] = __ldg(q + off[m]);
+        }
+    };
+    load_row(rowp);
+    for (int base = r0; base < r1 + K - 1; base += K) {
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+            const int ri = base + u;
+            if (ri < r1 + K - 1) {
+                uint32_t w[M + 1];
+#pragma unroll
+                for (int m = 0; m <= M; ++m) w[m] = wn[m];
+                rowp += pitch_w;
+                if (ri + 1 < r1 + K - 1) load_row(rowp);
+                // byte-shifted windows: sw[b][m] = bytes [4m+b, 4m+b+4) of the thread's window
+                uint32_t sw[4][M];
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    sw[0][m] = w[m];
+                    sw[1][m] = __byte_perm(w[m], w[m + 1], 0x4321);
+                    sw[2][m] = __byte_perm(w[m], w[m + 1], 0x5432);
+                    sw[3][m] = __byte_perm(w[m], w[m + 1], 0x6543);
+                }
+                if (SEPARABLE) {
+                    int32_t h[4];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        int32_t a = 0;
+#pragma unroll
+                        for (int m = 0; m < M; ++m) a = dp4a_us(sw[b][m], taps.t[m], a);
+                        h[b] = a;
+                    }
+#pragma unroll
+                    for (int kr = 0; kr < K; ++kr)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) acc[(u - kr + K) % K][b] += h[b] * taps.u[kr];
+                } else {
+#pragma unroll
+                    for (int kr = 0; kr < K; ++kr)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            int32_t a = acc[(u - kr + K) % K][b];
+#pragma unroll
+                            for (int m = 0; m < M; ++m) a = dp4a_us(sw[b][m], taps.t[kr * M + m], a);
+                            acc[(u - kr + K) % K][b] = a;
+                        }
+                }
+                const int ro = ri - (K - 1);                  // this output row has now seen all of its K input rows
+                if (ro >= r0) {
+                    int32_t q[4];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) q[b] = conv_div<DIVMODE>(acc[(u + 1) % K][b], p.norm, magic, shift);
+                    if (p.out_is_u8) {
+                        uint8_t *o = reinterpret_cast<uint8_t *>(p.out) + (size_t)ro * p.out_pitch + 4 * jw;
+                        if (full && (((uintptr_t)o) & 3) == 0)
+                            *reinterpret_cast<uint32_t *>(o) = (uint32_t)(q[0] & 255) | ((uint32_t)(q[1] & 255) << 8) | ((uint32_t)(q[2] & 255) << 16) | ((uint32_t)q[3] << 24);
+                        else
+                            for (int b = 0; b < 4; ++b) if (4 * jw + b < p.cols3) o[b] = (uint8_t)q[b];
+                    } else {
+                        int32_t *o = reinterpret_cast<int32_t *>(reinterpret_cast<uint8_t *>(p.out) + (size_t)ro * p.out_pitch) + 4 * jw;
+                        if (full && (((uintptr_t)o) & 15) == 0) *reinterpret_cast<int4 *>(o) = make_int4(q[0], q[1], q[2], q[3]);
+                        else
+                            for (int b = 0; b < 4; ++b) if (4 * jw + b < p.cols3) o[b] = q[b];
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[(u + 1) % K][b] = 0;
+            }
+        }
+    }
+}
+
+template <int K, bool SEP>
+static void launch_word(const ConvParams &p, const ConvWordTaps &t, int divmode, uint32_t magic, int shift, dim3 grid, cudaStream_t st) {
+    count_launch();
+    if (divmode == 0) conv_word_kernel<K, SEP, 0><<<grid, 256, 0, st>>>(p, t, magic, shift);
+    else if (divmode == 1) conv_word_kernel<K, SEP, 1><<<grid, 256, 0, st>>>(p, t, magic, shift);
+    else conv_word_kernel<K, SEP, 2><<<grid, 256, 0, st>>>(p, t, magic, shift);
+}
+
 // any K up to CONV_MAX_K without unrolling (odd sizes nobody benchmarks): one thread per output
 template <typename ACC>
 __global__ void __launch_bounds__(256) conv_direct_kernel(const ConvParams p, const ConvTaps taps, int K) {
@@ -149,6 +292,46 @@ cudaError_t launch_conv(const uint8_t *in, size_t in_pitch, int rows, int cols, 
     if (sep) { for (int i = 0; i < K; ++i) { taps.t[i] = u[i]; taps.t[K + i] = v[i]; } }
     else for (int i = 0; i < K * K; ++i) taps.t[i] = taps_host[i];
 
+    // ---- word-wide dp4a path
+    bool bytes_ok = true, nonneg = true;
+    for (int i = 0; i < K * K; ++i) { nonneg = nonneg && taps_host[i] >= 0; }
+    if (sep) { for (int i = 0; i < K; ++i) bytes_ok = bytes_ok && v[i] >= -127 && v[i] <= 127; }
+    else for (int i = 0; i < K * K; ++i) bytes_ok = bytes_ok && taps_host[i] >= -127 && taps_host[i] <= 127;
+    if ((K == 3 || K == 5 || K == 7 || K == 9) && !wide && bytes_ok && (((uintptr_t)in | in_pitch) & 3) == 0) {
+        const int M = conv_m(K);
+        ConvWordTaps wt{};
+        auto dilate = [&](const int32_t *row, uint32_t *dst) {          // tap kc -> byte 3*kc of the M tap words
+            for (int m = 0; m < M; ++m) dst[m] = 0;
+            for (int kc = 0; kc < K; ++kc) dst[(3 * kc) >> 2] |= (uint32_t)(row[kc] & 255) << (8 * ((3 * kc) & 3));
+        };
+        if (sep) { for (int i = 0; i < K; ++i) wt.u[i] = u[i]; dilate(v, wt.t); }
+        else for (int kr = 0; kr < K; ++kr) dilate(taps_host + kr * K, wt.t + kr * M);
+        int divmode = 2, shift = 0;
+        uint32_t magic = 0;
+        if (nonneg && norm > 0) {
+            if ((norm & (norm - 1)) == 0) { divmode = 0; while ((1 << shift) < norm) ++shift; }
+            else {
+                // floor(a / norm) = umulhi(a, magic) >> shift for every 0 <= a < 2^31 (round-up method, 33-bit-free because a < 2^31)
+                int l = 0;
+                while ((1LL << l) < norm) ++l;
+                const unsigned long long m64 = ((1ULL << (31 + l)) + (unsigned long long)norm - 1) / (unsigned long long)norm;
+                if (m64 < (1ULL << 32)) { divmode = 1; magic = (uint32_t)m64; shift = l - 1; }
+            }
+        }
+        const int nwords = (p.cols3 + 3) / 4;
+        const int gx = (nwords + 255) / 256;
+        int bands = (int)max(1LL, min((long long)(rows + 8 * K - 1) / (8 * K), ((long long)sm_count * 16 + gx - 1) / gx));
+        p.band_rows = (rows + bands - 1) / bands;
+        bands = (rows + p.band_rows - 1) / p.band_rows;
+        const dim3 grid(gx, bands);
+        switch (K) {
+            case 3: sep ? launch_word<3, true>(p, wt, divmode, magic, shift, grid, st) : launch_word<3, false>(p, wt, divmode, magic, shift, grid, st); break;
+            case 5: sep ? launch_word<5, true>(p, wt, divmode, magic, shift, grid, st) : launch_word<5, false>(p, wt, divmode, magic, shift, grid, st); break;
+            case 7: sep ? launch_word<7, true>(p, wt, divmode, magic, shift, grid, st) : launch_word<7, false>(p, wt, divmode, magic, shift, grid, st); break;
+            case 9: sep ? launch_word<9, true>(p, wt, divmode, magic, shift, grid, st) : launch_word<9, false>(p, wt, divmode, magic, shift, grid, st); break;
+        }
+        return cudaGetLastError();
+    }
     const bool unrolled = (K == 3 || K == 5 || K == 7 || K == 9) && !wide;
     if (unrolled) {
         const int gx = (p.cols3 + 255) / 256;

@@ -581,14 +581,15 @@ extern "C" int ompimg_conv_i32_host(const uint8_t *in_padded, int rows, int cols
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     NEED(in_padded && out && taps && rows > 0 && cols > 0, "image");
     NEED(K >= 1 && K <= 15 && norm != 0, "K in 1..15, norm != 0");
-    const size_t in_row = (size_t)(cols + K - 1) * 3, in_bytes = in_row * (rows + K - 1);
-    const size_t out_row = (size_t)cols * 3 * sizeof(int32_t), out_bytes = out_row * rows;
-    RESERVE(g.scratch[0], in_bytes + 256);
+    const size_t in_row = (size_t)(cols + K - 1) * 3, in_rows = (size_t)rows + K - 1;
+    const size_t in_pitch = round_up(in_row, 128);                 // aligned rows: the dp4a kernel loads 32-bit words
+    const size_t out_row = (size_t)cols * 3 * sizeof(int32_t), out_pitch = round_up(out_row, 128), out_bytes = out_pitch * rows;
+    RESERVE(g.scratch[0], in_pitch * in_rows + 256);
     RESERVE(g.scratch[1], out_bytes + 256);
     cudaStream_t st = g.streams[0];
-    CK(cudaMemcpyAsync(g.scratch[0].p, in_padded, in_bytes, cudaMemcpyHostToDevice, st));
-    CK(launch_conv((const uint8_t *)g.scratch[0].p, in_row, rows, cols, K, taps, norm, g.scratch[1].p, out_row, 0, g.sm_count, st));
-    CK(cudaMemcpyAsync(out, g.scratch[1].p, out_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpy2DAsync(g.scratch[0].p, in_pitch, in_padded, in_row, in_row, in_rows, cudaMemcpyHostToDevice, st));
+    CK(launch_conv((const uint8_t *)g.scratch[0].p, in_pitch, rows, cols, K, taps, norm, g.scratch[1].p, out_pitch, 0, g.sm_count, st));
+    CK(cudaMemcpy2DAsync(out, out_row, g.scratch[1].p, out_pitch, out_row, rows, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return OMPIMG_OK;
 }
