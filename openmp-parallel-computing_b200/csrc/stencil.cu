@@ -12,6 +12,8 @@
 //
 // Row-band mode (ompimg_bands_*): the rows just above/below the band live on a peer GPU; the
 // producer warp fetches them with ordinary global loads through the NVLink peer mapping.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -31,6 +33,7 @@ struct StencilParams {
     uint32_t stage_bytes;   // three row slots
     uint32_t row_slot;      // bytes reserved per row in a stage (16-byte halo blocks included)
     uint32_t row_bytes16;   // round16(width*bpp)
+    int relaxed;            // consumers sleep (instead of re-probing) when their stage is not refilled yet
 };
 
 template <int CH>
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32, CH == 1 ? 3 : 2) sobel_r
         const uint32_t stage = my + so + (uint32_t)rho * row_slot;
         // (a warp that finds its stage not yet refilled is ahead of the slowest warp of the CTA -- the ring is only
         // refilled when every warp has released a stage; sleeping there instead of re-probing measured the same)
-        if (rho == 0) mbar_wait(fb, ph);
+        if (rho == 0) { if (p.relaxed) mbar_wait_relaxed(fb, ph); else mbar_wait(fb, ph); }
         uint32_t P[8], Q[9];
         if (CH == 1) {
             const uint32_t C64 = 0x64646464u;
@@ -297,6 +300,7 @@ static cudaError_t launch_sobel_t(const StencilArgs &a, int sm_count, cudaStream
     p.src_stride = a.src_stride; p.dst_stride = a.dst_stride;
     p.halo_above = a.halo_above; p.halo_below = a.halo_below;
     p.width = a.width; p.height = a.height;
+    { static int relaxed = -1; if (relaxed < 0) { const char *e = getenv("OMPIMG_RELAXED_WAIT"); relaxed = e ? atoi(e) : 0; } p.relaxed = relaxed; }
     p.nw = min(ST_MAX_NW, (a.width + 511) / 512);
     const int nstrips = (a.width + p.nw * 512 - 1) / (p.nw * 512);
     p.row_bytes16 = (uint32_t)(((size_t)a.width * CH + 15) & ~(size_t)15);

@@ -332,6 +332,31 @@ def test_row_bands_equal_single_pass(gpu, O):
     b.close()
 
 
+@pytest.mark.parametrize("ch", [1, 3])
+def test_band_entry_point_with_explicit_halo_rows(gpu, O, ch):
+    """ompimg_rgb_to_edge_band_dev: what a rank of the one-process-per-GPU row-band mode calls after it has
+    received its neighbours' rows (bands_mp.py); three bands with halo buffers reproduce the whole image."""
+    L = gpu.lib()
+    w, h = 1100, 151
+    img = O.synth(h * w * ch, 0xB2000055 + ch).reshape(h, w * ch)
+    whole = O.rgb_to_edge(img.reshape(h, w, 3)) if ch == 3 else O.sobel(img)
+    pitch, ep = (w * ch + 127) // 128 * 128, (w + 127) // 128 * 128
+    got = np.zeros((h, w), np.uint8)
+    bounds = [0, 47, 48, h]                                            # a one-row band in the middle as well
+    for r0, r1 in zip(bounds, bounds[1:]):
+        band = to_dev_pitched(gpu, img[r0:r1], pitch)
+        above = to_dev_pitched(gpu, img[r0 - 1:r0], pitch) if r0 > 0 else None
+        below = to_dev_pitched(gpu, img[r1:r1 + 1], pitch) if r1 < h else None
+        edge = gpu.DeviceBuffer(ep * (r1 - r0) + 64)
+        edge.fill(0)
+        ck(gpu, L.ompimg_rgb_to_edge_band_dev(band.ptr, pitch, ch, edge.ptr, ep, w, r1 - r0,
+                                             above.ptr if above else None, below.ptr if below else None, 0))
+        gpu.sync(0)
+        got[r0:r1] = from_dev_pitched(gpu, edge, r1 - r0, ep, ep)[:, :w]
+    assert np.array_equal(got[1:-1, 1:-1], whole[1:-1, 1:-1])
+    assert not got[0].any() and not got[-1].any() and not got[:, 0].any() and not got[:, -1].any()
+
+
 # ------------------------------------------------------------------------------------------------ old/ kernels
 @pytest.mark.parametrize("key", ["37_53_5_273", "64_96_9_81", "24_31_3_16", "48_40_5_25"])
 def test_old_kernels_golden(gpu, O, golden, key):
