@@ -2,11 +2,14 @@
 // device memory, timers, the device-resident entry points, the host-buffer pipelines and the two
 // frozen reference prototypes.
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/ompimg_b200.h"
@@ -40,6 +43,8 @@ struct Ctx {
     std::vector<Timer> timers;
     DevBuf scratch[4];                       // host-API staging on the device
     DevBuf slots[OMPIMG_NUM_STREAMS][2];     // per-stream (input, output) slots of the batch pipeline
+    DevBuf pin[3];                           // pinned host staging for pageable caller buffers (grow-only)
+    std::vector<cudaEvent_t> chunk_events;   // one per in-flight chunk of a staged download
     std::recursive_mutex mu;
 };
 Ctx g;
@@ -107,6 +112,97 @@ int reserve(DevBuf &b, size_t bytes) {
 
 inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// A few persistent helper threads for the staging copies between the caller's pageable buffer and the
+// pinned staging buffer: one core moves ~10 GB/s, which is below what the two PCIe directions carry.
+class CopyPool {
+  public:
+    void copy(void *dst, const void *src, size_t bytes) {
+        if (bytes < (256u << 10) || nthreads() == 0) { memcpy(dst, src, bytes); return; }
+        const int parts = nthreads() + 1;
+        const size_t step = ((bytes + parts - 1) / parts + 4095) & ~(size_t)4095;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            dst_ = (uint8_t *)dst; src_ = (const uint8_t *)src; bytes_ = bytes; step_ = step;
+            pending_ = nthreads();
+            ++generation_;
+        }
+        cv_.notify_all();
+        part(0);                                   // the caller takes the first slice
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+
+  private:
+    int nthreads() {
+        if (!started_) {
+            started_ = true;
+            const char *e = getenv("OMPIMG_COPY_THREADS");
+            int n = e ? atoi(e) : 3;
+            if (n < 0) n = 0;
+            if (n > 15) n = 15;
+            for (int i = 0; i < n; ++i) workers_.emplace_back([this, i] { run(i + 1); });
+        }
+        return (int)workers_.size();
+    }
+    void part(int idx) {
+        const size_t lo = (size_t)idx * step_;
+        if (lo < bytes_) memcpy(dst_ + lo, src_ + lo, bytes_ - lo < step_ ? bytes_ - lo : step_);
+    }
+    void run(int idx) {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_;
+            }
+            part(idx);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    uint8_t *dst_ = nullptr;
+    const uint8_t *src_ = nullptr;
+    size_t bytes_ = 0, step_ = 0;
+    int pending_ = 0;
+    unsigned long long generation_ = 0;
+    bool stop_ = false, started_ = false;
+};
+CopyPool g_copy;
+
+int reserve_pinned(DevBuf &b, size_t bytes) {
+    if (b.cap >= bytes) return OMPIMG_OK;
+    if (b.p) { CK(cudaDeviceSynchronize()); CK(cudaFreeHost(b.p)); b.p = nullptr; b.cap = 0; }
+    const size_t want = (bytes + (1 << 20) - 1) & ~(size_t)((1 << 20) - 1);
+    cudaError_t e = cudaHostAlloc(&b.p, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) { b.p = nullptr; return fail(OMPIMG_ERR_NOMEM, "cudaHostAlloc(%zu): %s", want, cudaGetErrorString(e)); }
+    b.cap = want;
+    return OMPIMG_OK;
+}
+#define RESERVE_PIN(buf, bytes)                     \
+    do {                                            \
+        int rc_ = reserve_pinned((buf), (bytes));   \
+        if (rc_ != OMPIMG_OK) return rc_;           \
+    } while (0)
+
+int need_events(size_t n) {
+    while (g.chunk_events.size() < n) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        g.chunk_events.push_back(e);
+    }
+    return OMPIMG_OK;
+}
+
 bool is_pinned(const void *p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -136,14 +232,24 @@ extern "C" int ompimg_init(int device) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (g.ready && g.device == device) return OMPIMG_OK;
     if (g.ready) return fail(OMPIMG_ERR_ARG, "already bound to device %d", g.device);
+    const bool verbose = getenv("OMPIMG_VERBOSE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (verbose) fprintf(stderr, "[ompimg_b200] init: %-28s +%.1f ms\n", what,
+                             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+    };
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0)
         return fail(OMPIMG_ERR_CUDA, "no usable CUDA device (%s); libompimg_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count=0");
     NEED(device >= 0 && device < n, "device index");
+    lap("cudaGetDeviceCount");
     CK(cudaSetDevice(device));
+    CK(cudaFree(nullptr));                       // create the context now
+    lap("context");
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
+    lap("device properties");
     if (prop.major < 10) return fail(OMPIMG_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     g.sm_count = prop.multiProcessorCount;
     for (int i = 0; i < OMPIMG_NUM_STREAMS; ++i) {
@@ -152,6 +258,7 @@ extern "C" int ompimg_init(int device) {
     }
     const char *m = getenv("OMPIMG_LUMA");
     if (m) g.luma_mode = (!strcmp(m, "fma") || !strcmp(m, "1")) ? OMPIMG_LUMA_FMA : OMPIMG_LUMA_STRICT;
+    lap("streams");
     g.device = device;
     g.ready = true;
     // The Sobel kernels truncate sqrt.approx(m).  Whether that equals isqrt(m) at the perfect squares
@@ -173,6 +280,7 @@ extern "C" int ompimg_init(int device) {
             g.sqrt_exact = ok ? 1 : 0;
         }
     }
+    lap("sqrt check");
     return OMPIMG_OK;
 }
 namespace ompimg {
@@ -202,6 +310,9 @@ extern "C" int ompimg_shutdown(void) {
     cudaDeviceSynchronize();
     for (auto &b : g.scratch) { if (b.p) cudaFree(b.p); b = DevBuf(); }
     for (auto &s : g.slots) for (auto &b : s) { if (b.p) cudaFree(b.p); b = DevBuf(); }
+    for (auto &b : g.pin) { if (b.p) cudaFreeHost(b.p); b = DevBuf(); }
+    for (auto e : g.chunk_events) cudaEventDestroy(e);
+    g.chunk_events.clear();
     for (auto &t : g.timers) { if (t.a) cudaEventDestroy(t.a); if (t.b) cudaEventDestroy(t.b); }
     g.timers.clear();
     for (int i = 0; i < OMPIMG_NUM_STREAMS; ++i) { cudaStreamDestroy(g.streams[i]); cudaEventDestroy(g.edge_events[i]); }
@@ -458,9 +569,15 @@ extern "C" int ompimg_selftest_isqrt(uint8_t *out_host, unsigned int count, floa
 // =================================================================================================
 // host-buffer pipelines
 // =================================================================================================
-// a1 through host memory: the image is cut into chunks of whole 16-pixel groups; chunk i goes
-// H2D -> kernel -> D2H on stream i % NS, so the upload of one chunk overlaps the kernel and the
-// download of the previous ones (PCIe is full duplex).
+// Pageable caller memory (what stbi_load returns, main.c:21) cannot be the source of a truly asynchronous
+// copy, and registering it per call costs more than the copy.  The host pipelines therefore stage it
+// through a pinned buffer owned by the library: the host thread memcpy's chunk i+1 into the staging
+// buffer while the DMA engines move chunk i (H2D) and chunk i-1 (D2H) and the kernel runs in between.
+// Caller buffers that are already pinned (ompimg_host_alloc, OMPIMG_PIN=register) skip the staging copy.
+constexpr size_t STAGE_CHUNK = 1 << 20;
+constexpr int STAGE_STREAMS = 4;
+
+// a1 through host memory: chunks of whole 16-pixel groups go H2D -> kernel -> D2H on rotating streams.
 extern "C" int ompimg_gray_inplace_host(uint8_t *data, int w, int h, int ch) {
     INIT();
     std::lock_guard<std::recursive_mutex> lk(g.mu);
@@ -468,22 +585,34 @@ extern "C" int ompimg_gray_inplace_host(uint8_t *data, int w, int h, int ch) {
     NEED(ch == 3 || ch == 4, "channels must be 3 or 4 (1 and 2 are undefined behaviour in the reference)");
     const size_t npx = (size_t)w * h, bytes = npx * ch;
     ScopedPin pin(data, bytes);
+    const bool direct = is_pinned(data);
     RESERVE(g.scratch[0], bytes + 256);
     uint8_t *d = (uint8_t *)g.scratch[0].p;
-    const size_t min_chunk_px = 256 * 1024;           // >= 0.75 MB per copy
-    size_t nchunks = npx / min_chunk_px;
+    uint8_t *hp = data;
+    if (!direct) { RESERVE_PIN(g.pin[0], bytes); hp = (uint8_t *)g.pin[0].p; }
+    size_t nchunks = bytes / STAGE_CHUNK;
     if (nchunks < 1) nchunks = 1;
-    if (nchunks > 2 * OMPIMG_NUM_STREAMS) nchunks = 2 * OMPIMG_NUM_STREAMS;
+    if (nchunks > 64) nchunks = 64;
     const size_t chunk_px = round_up((npx + nchunks - 1) / nchunks, 16);
-    int i = 0;
+    nchunks = (npx + chunk_px - 1) / chunk_px;
+    int rc = need_events(nchunks);
+    if (rc) return rc;
+    size_t i = 0;
     for (size_t p0 = 0; p0 < npx; p0 += chunk_px, ++i) {
         const size_t n = npx - p0 < chunk_px ? npx - p0 : chunk_px;
-        cudaStream_t st = g.streams[i % OMPIMG_NUM_STREAMS];
-        CK(cudaMemcpyAsync(d + p0 * ch, data + p0 * ch, n * ch, cudaMemcpyHostToDevice, st));
+        cudaStream_t st = g.streams[i % STAGE_STREAMS];
+        if (!direct) g_copy.copy(hp + p0 * ch, data + p0 * ch, n * ch);
+        CK(cudaMemcpyAsync(d + p0 * ch, hp + p0 * ch, n * ch, cudaMemcpyHostToDevice, st));
         CK(launch_gray_inplace(d + p0 * ch, n * ch, (int)n, 1, ch, 1, 0, g.luma_mode, g.sm_count, st));
-        CK(cudaMemcpyAsync(data + p0 * ch, d + p0 * ch, n * ch, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hp + p0 * ch, d + p0 * ch, n * ch, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(g.chunk_events[i], st));
     }
-    for (int s = 0; s < OMPIMG_NUM_STREAMS && s < i; ++s) CK(cudaStreamSynchronize(g.streams[s]));
+    i = 0;
+    for (size_t p0 = 0; p0 < npx; p0 += chunk_px, ++i) {
+        const size_t n = npx - p0 < chunk_px ? npx - p0 : chunk_px;
+        CK(cudaEventSynchronize(g.chunk_events[i]));
+        if (!direct) g_copy.copy(data + p0 * ch, hp + p0 * ch, n * ch);
+    }
     return OMPIMG_OK;
 }
 
@@ -495,27 +624,43 @@ extern "C" int ompimg_sobel_host(const uint8_t *src, uint8_t *dst, int w, int h)
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     NEED(src && dst && w > 0 && h > 0, "image");
     if (w < 3 || h < 3) return OMPIMG_OK;              // sobel.c:11-12: no interior, nothing written
-    const size_t pitch = round_up((size_t)w, 128);
-    ScopedPin pin_s(src, (size_t)w * h), pin_d(dst, (size_t)w * h);
+    const size_t pitch = round_up((size_t)w, 128), plane = (size_t)w * h;
+    ScopedPin pin_s(src, plane), pin_d(dst, plane);
+    const bool src_direct = is_pinned(src), dst_direct = is_pinned(dst);
     RESERVE(g.scratch[0], pitch * h + 256);
     RESERVE(g.scratch[1], pitch * h + 256);
     uint8_t *ds = (uint8_t *)g.scratch[0].p, *dd = (uint8_t *)g.scratch[1].p;
+    const uint8_t *hs = src;
+    uint8_t *hd = dst;
+    if (!src_direct) { RESERVE_PIN(g.pin[0], plane); hs = (const uint8_t *)g.pin[0].p; }
+    if (!dst_direct) { RESERVE_PIN(g.pin[1], plane); hd = (uint8_t *)g.pin[1].p; }
     const int interior = h - 2;
-    int nb = (int)(((size_t)w * h) / (1 << 20));
+    int nb = (int)(plane / STAGE_CHUNK);
     if (nb < 1) nb = 1;
-    if (nb > OMPIMG_NUM_STREAMS) nb = OMPIMG_NUM_STREAMS;
+    if (nb > 32) nb = 32;
     const int rows_per = (interior + nb - 1) / nb;
+    nb = (interior + rows_per - 1) / rows_per;
+    int rc = need_events(nb);
+    if (rc) return rc;
     int i = 0;
     for (int y0 = 1; y0 < h - 1; y0 += rows_per, ++i) {
         const int y1 = y0 + rows_per < h - 1 ? y0 + rows_per : h - 1;   // output rows [y0, y1)
-        cudaStream_t st = g.streams[i % OMPIMG_NUM_STREAMS];
+        cudaStream_t st = g.streams[i % STAGE_STREAMS];
         const int r0 = y0 - 1, nr = y1 - y0 + 2;                          // source rows incl. halo
-        CK(cudaMemcpy2DAsync(ds + (size_t)r0 * pitch, pitch, src + (size_t)r0 * w, w, w, nr, cudaMemcpyHostToDevice, st));
-        int rc = sobel_common(ds + (size_t)r0 * pitch, pitch, 1, dd + (size_t)r0 * pitch, pitch, w, nr, 1, 0, 0, nullptr, nullptr, st);
+        if (!src_direct) g_copy.copy((uint8_t *)g.pin[0].p + (size_t)r0 * w, src + (size_t)r0 * w, (size_t)nr * w);
+        CK(cudaMemcpy2DAsync(ds + (size_t)r0 * pitch, pitch, hs + (size_t)r0 * w, w, w, nr, cudaMemcpyHostToDevice, st));
+        rc = sobel_common(ds + (size_t)r0 * pitch, pitch, 1, dd + (size_t)r0 * pitch, pitch, w, nr, 1, 0, 0, nullptr, nullptr, st);
         if (rc) return rc;
-        CK(cudaMemcpy2DAsync(dst + (size_t)y0 * w + 1, w, dd + (size_t)y0 * pitch + 1, pitch, w - 2, y1 - y0, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpy2DAsync(hd + (size_t)y0 * w + 1, w, dd + (size_t)y0 * pitch + 1, pitch, w - 2, y1 - y0, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(g.chunk_events[i], st));
     }
-    for (int s = 0; s < OMPIMG_NUM_STREAMS && s < i; ++s) CK(cudaStreamSynchronize(g.streams[s]));
+    i = 0;
+    for (int y0 = 1; y0 < h - 1; y0 += rows_per, ++i) {
+        const int y1 = y0 + rows_per < h - 1 ? y0 + rows_per : h - 1;
+        CK(cudaEventSynchronize(g.chunk_events[i]));
+        if (!dst_direct)
+            for (int y = y0; y < y1; ++y) memcpy(dst + (size_t)y * w + 1, hd + (size_t)y * w + 1, (size_t)w - 2);
+    }
     return OMPIMG_OK;
 }
 
@@ -527,18 +672,47 @@ extern "C" int ompimg_gray_sobel_pass_host(uint8_t *img, int w, int h, int ch, u
     NEED(ch == 3 || ch == 4, "channels must be 3 or 4");
     const size_t row = (size_t)w * ch, ipitch = round_up(row, 128), epitch = round_up((size_t)w, 128);
     ScopedPin pin_i(img, row * h);
+    const bool direct = is_pinned(img);
     RESERVE(g.scratch[0], ipitch * h + 256);
     RESERVE(g.scratch[1], epitch * h + 256);
     uint8_t *di = (uint8_t *)g.scratch[0].p, *de = (uint8_t *)g.scratch[1].p;
+    uint8_t *hi = img;
+    if (!direct) { RESERVE_PIN(g.pin[0], row * h); hi = (uint8_t *)g.pin[0].p; }
     cudaStream_t st = g.streams[0];
-    CK(cudaMemcpy2DAsync(di, ipitch, img, row, row, h, cudaMemcpyHostToDevice, st));
-    if (edge) CK(cudaMemcpy2DAsync(de, epitch, edge, w, w, h, cudaMemcpyHostToDevice, st));   // the scratch plane's border survives the pass
-    else CK(cudaMemsetAsync(de, 0, epitch * h, st));
-    int rc = sobel_common(di, ipitch, ch, de, epitch, w, h, 1, 0, 0, nullptr, nullptr, st);
+    // the scratch plane's border survives the pass (main_with_sobel.c:37): only a non-zero border has to travel
+    bool zero_border = true;
+    if (edge) {
+        for (int x = 0; x < w && zero_border; ++x) zero_border = !edge[x] && !edge[(size_t)(h - 1) * w + x];
+        for (int y = 0; y < h && zero_border; ++y) zero_border = !edge[(size_t)y * w] && !edge[(size_t)y * w + w - 1];
+    }
+    if (zero_border) CK(cudaMemsetAsync(de, 0, epitch * h, st));
+    else CK(cudaMemcpy2DAsync(de, epitch, edge, w, w, h, cudaMemcpyHostToDevice, st));
+    int rows_per = (int)(STAGE_CHUNK / row);
+    if (rows_per < 1) rows_per = 1;
+    const int nb = (h + rows_per - 1) / rows_per;
+    int rc = need_events(nb);
+    if (rc) return rc;
+    for (int y0 = 0; y0 < h; y0 += rows_per) {
+        const int nr = y0 + rows_per < h ? rows_per : h - y0;
+        if (!direct) g_copy.copy(hi + (size_t)y0 * row, img + (size_t)y0 * row, (size_t)nr * row);
+        CK(cudaMemcpy2DAsync(di + (size_t)y0 * ipitch, ipitch, hi + (size_t)y0 * row, row, row, nr, cudaMemcpyHostToDevice, st));
+    }
+    rc = sobel_common(di, ipitch, ch, de, epitch, w, h, 1, 0, 0, nullptr, nullptr, st);
     if (rc) return rc;
     CK(launch_replicate(de, epitch, di, ipitch, ch, w, h, 1, 0, 0, g.sm_count, st));
-    CK(cudaMemcpy2DAsync(img, row, di, ipitch, row, h, cudaMemcpyDeviceToHost, st));
+    int i = 0;
+    for (int y0 = 0; y0 < h; y0 += rows_per, ++i) {
+        const int nr = y0 + rows_per < h ? rows_per : h - y0;
+        CK(cudaMemcpy2DAsync(hi + (size_t)y0 * row, row, di + (size_t)y0 * ipitch, ipitch, row, nr, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(g.chunk_events[i], st));
+    }
     if (edge) CK(cudaMemcpy2DAsync(edge, w, de, epitch, w, h, cudaMemcpyDeviceToHost, st));
+    i = 0;
+    for (int y0 = 0; y0 < h; y0 += rows_per, ++i) {
+        const int nr = y0 + rows_per < h ? rows_per : h - y0;
+        CK(cudaEventSynchronize(g.chunk_events[i]));
+        if (!direct) g_copy.copy(img + (size_t)y0 * row, hi + (size_t)y0 * row, (size_t)nr * row);
+    }
     CK(cudaStreamSynchronize(st));
     return OMPIMG_OK;
 }
