@@ -63,7 +63,7 @@ class Dist:
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
         self.td = None
-        if self.world > 1:
+        if self.world > 1 and backend:
             import torch
             import torch.distributed as td
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -427,7 +427,7 @@ def main():
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
-    dist = Dist("gloo" if args.impl == "reference" else args.backend)
+    dist = Dist(None if args.impl == "reference" else args.backend)      # the reference arm runs on rank 0 alone: no process group
     try:
         if args.impl == "reference":
             run_reference(args, dist)
