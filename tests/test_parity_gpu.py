@@ -332,6 +332,32 @@ def test_row_bands_equal_single_pass(gpu, O):
     b.close()
 
 
+@pytest.mark.parametrize("w", [17, 511, 512, 513, 2047, 4096, 4097, 4112, 8191])
+@pytest.mark.parametrize("h", [3, 4, 5, 6, 7, 17, 130, 131, 132, 133, 134, 262, 263, 264])
+def test_sobel_and_fused_tricky_shapes(gpu, O, w, h):
+    """shapes around the kernel's internal boundaries: 512-column warps, 4096-column strips, 16-pixel groups,
+    three-row trips and the 130/64/34/16-row bands (first band one row taller)"""
+    if w > 4200 and h > 140:
+        pytest.skip("covered by the smaller combinations")
+    L = gpu.lib()
+    seed = w * 1000 + h
+    for ch in (1, 3):
+        src = O.synth(h * w * ch, seed + ch).reshape(h, w * ch)
+        want = O.sobel(src, np.full((h, w), 0x5A, np.uint8)) if ch == 1 else O.rgb_to_edge(src.reshape(h, w, 3), np.full((h, w), 0x5A, np.uint8))
+        sp, ep = (w * ch + 127) // 128 * 128, (w + 127) // 128 * 128
+        sbuf = to_dev_pitched(gpu, src, sp)
+        ebuf = gpu.DeviceBuffer(ep * h + 64)
+        ebuf.fill(0x5A)
+        if ch == 1:
+            ck(gpu, L.ompimg_sobel_dev(sbuf.ptr, sp, ebuf.ptr, ep, w, h, 1, 0, 0, 0))
+        else:
+            ck(gpu, L.ompimg_rgb_to_edge_dev(sbuf.ptr, sp, 3, ebuf.ptr, ep, w, h, 1, 0, 0, 0))
+        got = from_dev_pitched(gpu, ebuf, h, ep, ep)
+        assert np.array_equal(got[:, :w], want), (w, h, ch)
+        assert np.all(got[:, w:] == 0x5A)
+        sbuf.free(); ebuf.free()
+
+
 @pytest.mark.parametrize("ch", [1, 3])
 def test_band_entry_point_with_explicit_halo_rows(gpu, O, ch):
     """ompimg_rgb_to_edge_band_dev: what a rank of the one-process-per-GPU row-band mode calls after it has
