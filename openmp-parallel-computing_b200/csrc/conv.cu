@@ -292,6 +292,12 @@ cudaError_t launch_conv(const uint8_t *in, size_t in_pitch, int rows, int cols, 
     if (sep) { for (int i = 0; i < K; ++i) { taps.t[i] = u[i]; taps.t[K + i] = v[i]; } }
     else for (int i = 0; i < K * K; ++i) taps.t[i] = taps_host[i];
 
+    // ---- rank-1 taps in range: the planar dp4a/dp2a kernel of conv_sep.cu
+    if (sep) {
+        cudaError_t e = cudaSuccess;
+        if (launch_conv_sep(in, in_pitch, rows, cols, K, u, v, norm, out, out_pitch, out_is_u8, sm_count, st, &e)) return e;
+    }
+
     // ---- word-wide dp4a path
     bool bytes_ok = true, nonneg = true;
     for (int i = 0; i < K * K; ++i) { nonneg = nonneg && taps_host[i] >= 0; }

@@ -63,4 +63,8 @@ cudaError_t launch_isqrt_selftest(uint8_t *out_dev, unsigned int count, float bi
 cudaError_t launch_conv(const uint8_t *in, size_t in_pitch, int rows, int cols, int K, const int32_t *taps_host, int32_t norm,
                         void *out, size_t out_pitch, int out_is_u8, int sm_count, cudaStream_t st);
 
+// conv_sep.cu: rank-1 taps u (vertical) x v (horizontal); false = outside its ranges, nothing launched
+bool launch_conv_sep(const uint8_t *in, size_t in_pitch, int rows, int cols, int K, const int32_t *u, const int32_t *v, int32_t norm,
+                     void *out, size_t out_pitch, int out_is_u8, int sm_count, cudaStream_t st, cudaError_t *err);
+
 }  // namespace ompimg

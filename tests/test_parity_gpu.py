@@ -416,6 +416,71 @@ def test_convolution_vs_oracle(gpu, O, K, kind):
     assert np.array_equal(gpu.parallel_convolution(padded, kern, norm), O.convolution_u8(padded, kern, norm))
 
 
+def _sep_kernel(K, kind):
+    b = np.array([1.0])
+    for _ in range(K - 1):
+        b = np.convolve(b, [1, 1])
+    b = b.astype(np.int64)
+    rng = np.random.default_rng(K * 7 + len(kind))
+    if kind == "box":
+        return np.ones((K, K), np.int64), K * K
+    if kind == "gauss":                               # norm 256 (K=5) / 65536 (K=9): the byte-select division
+        k = np.outer(b, b); return k, int(k.sum())
+    if kind == "gauss_half":                          # power-of-two norm that is not 2^8 / 2^16: plain shift
+        k = np.outer(b, b); return k, int(k.sum()) * 2
+    if kind == "pos_oddnorm":                         # positive rank-1 taps, norm not a power of two: multiply-high
+        u, v = rng.integers(0, 12, K), rng.integers(0, 9, K)
+        k = np.outer(u, v); return k, int(k.sum()) + 3
+    if kind == "signed":                              # derivative-like rank-1 taps: signed dp4a/dp2a and true division
+        u, v = rng.integers(-9, 10, K), rng.integers(-7, 8, K)
+        u[0], v[-1] = -3, 5
+        return np.outer(u, v), -37
+    if kind == "wide_v":                              # horizontal sums overflow 16 bits: falls back to conv.cu's kernels
+        u, v = np.ones(K, np.int64), np.full(K, 120, np.int64)
+        return np.outer(u, v), 1000
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("K", [3, 5, 7, 9])
+@pytest.mark.parametrize("kind", ["box", "gauss", "gauss_half", "pos_oddnorm", "signed", "wide_v"])
+def test_separable_convolution_device_layouts(gpu, O, K, kind):
+    """conv_sep.cu through the device entry points: dense and pitched rows at every 4-byte misalignment, widths
+    that end inside a warp / a lane, odd and tiny row counts, uint8 and int32 outputs with aligned and unaligned
+    output rows -- all against the oracle (old/parallel_convolution.c:8-24)."""
+    L = gpu.lib()
+    kern, norm = _sep_kernel(K, kind)
+    taps = np.ascontiguousarray(kern.reshape(-1), np.int32)
+    #        rows cols  in_pad in_off out_pad
+    cases = [(131, 517, 0, 0, 0), (64, 128, 4, 0, 0), (37, 1100, 20, 4, 16), (2, 3, 0, 8, 4), (1, 1, 0, 0, 0),
+             (200, 1024, 12, 12, 0), (75, 2100, 8, 0, 3), (33, 1028, 0, 0, 0)]
+    for (rows, cols, in_pad, in_off, out_pad) in cases:
+        pr, pc = rows + K - 1, cols + K - 1
+        padded = O.synth(pr * pc * 3, 0xC5E0 + K + rows).reshape(pr, pc, 3)
+        want = O.convolution_u8(padded, kern, norm)
+        in_row = pc * 3
+        in_pitch = (in_row + 3) // 4 * 4 + in_pad if in_pad else in_row
+        src = gpu.DeviceBuffer(in_off + in_pitch * pr + 64)
+        src.fill(0xEE)
+        assert L.ompimg_copy2d_h2d(src.ptr + in_off, in_pitch, padded.ctypes.data, in_row, in_row, pr, 0) == 0
+        for u8 in (True, False):
+            ob = 1 if u8 else 4
+            out_row = cols * 3 * ob
+            out_pitch = out_row + out_pad * ob
+            dst = gpu.DeviceBuffer(out_pitch * rows + 64)
+            dst.fill(0x5A)
+            fn = L.ompimg_conv_u8_dev if u8 else L.ompimg_conv_i32_dev
+            ck(gpu, fn(src.ptr + in_off, in_pitch, rows, cols, K, taps.ctypes.data, norm, dst.ptr, out_pitch, 0))
+            gpu.sync(0)
+            raw = dst.download(out_pitch * rows).reshape(rows, out_pitch)
+            got = raw[:, :out_row]
+            exp = want.astype(np.uint8).reshape(rows, out_row) if u8 else want.reshape(rows, cols * 3).view(np.uint8).reshape(rows, out_row)
+            assert np.array_equal(got, exp), (K, kind, rows, cols, in_pad, in_off, out_pad, u8)
+            assert (raw[:, out_row:] == 0x5A).all(), "bytes between output rows were written"
+            assert (dst.download(64, offset=out_pitch * rows) == 0x5A).all(), "bytes past the output were written"
+            dst.free()
+        src.free()
+
+
 def test_avg_and_gray3_accumulate_and_ragged(gpu, O):
     for (rows, cols) in [(1, 1), (7, 5), (33, 100), (240, 1001), (1080, 1920)]:
         img = O.synth(rows * cols * 3, rows + cols).reshape(rows, cols, 3)
