@@ -435,6 +435,8 @@ def _sep_kernel(K, kind):
         u, v = rng.integers(-9, 10, K), rng.integers(-7, 8, K)
         u[0], v[-1] = -3, 5
         return np.outer(u, v), -37
+    if kind == "vbox_pow2":                           # constant vertical taps with a power-of-two norm: window sums + shift
+        k = np.outer(np.full(K, 2, np.int64), b if K <= 5 else np.ones(K, np.int64)); return k, 64
     if kind == "wide_v":                              # horizontal sums overflow 16 bits: falls back to conv.cu's kernels
         u, v = np.ones(K, np.int64), np.full(K, 120, np.int64)
         return np.outer(u, v), 1000
@@ -442,7 +444,7 @@ def _sep_kernel(K, kind):
 
 
 @pytest.mark.parametrize("K", [3, 5, 7, 9])
-@pytest.mark.parametrize("kind", ["box", "gauss", "gauss_half", "pos_oddnorm", "signed", "wide_v"])
+@pytest.mark.parametrize("kind", ["box", "gauss", "gauss_half", "pos_oddnorm", "signed", "vbox_pow2", "wide_v"])
 def test_separable_convolution_device_layouts(gpu, O, K, kind):
     """conv_sep.cu through the device entry points: dense and pitched rows at every 4-byte misalignment, widths
     that end inside a warp / a lane, odd and tiny row counts, uint8 and int32 outputs with aligned and unaligned
