@@ -25,7 +25,7 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent
-LIB_PATH = HERE / "lib" / "libompimg_b200.so"
+LIB_PATH = Path(os.environ.get("OMPIMG_LIB", HERE / "lib" / "libompimg_b200.so"))   # OMPIMG_LIB: A/B builds while tuning
 NUM_STREAMS = 8
 LUMA_STRICT, LUMA_FMA = 0, 1
 

@@ -1,5 +1,7 @@
 // conv_sep.cu -- host side of the rank-1 convolution path: range checks, tap words, launch geometry.
 // The kernel is in conv_sep.cuh, instantiated per K in conv_sep_k{3,5,7,9}.cu.
+#include <cstdlib>
+
 #include "conv_sep.cuh"
 
 namespace ompimg {
@@ -64,7 +66,7 @@ bool launch_conv_sep(const uint8_t *in, size_t in_pitch, int rows, int cols, int
     p.rows = rows; p.cols = cols;
     p.in_row_bytes = (uint32_t)in_row;
     p.magic = magic; p.shift = shift; p.norm = norm;
-    p.out_bulk = (((uintptr_t)out | out_pitch) & 15) == 0;
+    p.out_wide = (((uintptr_t)out | out_pitch) & 15) == 0;
     for (int i = 0; i < 4; ++i)
         for (int m = 0; m < 3; ++m) {
             uint32_t wv = 0;
@@ -83,11 +85,15 @@ bool launch_conv_sep(const uint8_t *in, size_t in_pitch, int rows, int cols, int
     if (nstrips > 65535) return false;
     p.row_slot = (uint32_t)((16 + (SW + K - 1) * 3 + 16 + 127) & ~127);
     p.stage_bytes = 2 * p.row_slot;
-    p.stages = 4;
+    const int np = (K + 1) / 2;
+    p.stages = np >= 4 ? np : 2 * np;                      // a multiple of (K+1)/2, see the kernel
+    if (const char *e = getenv("OMPIMG_CONV_STAGES")) p.stages = np * max(1, min(4, atoi(e)));      // tuning knobs (tools/prof.py)
+    p.relaxed = 1;
+    if (const char *e = getenv("OMPIMG_CONV_RELAX")) p.relaxed = atoi(e);
     const int ob = out_is_u8 ? 1 : 4;
-    const int smem = p.stages * (int)p.stage_bytes + 16 * p.stages + 128 + p.nw * 4 * CS_WPX * 3 * ob;
+    const int smem = p.stages * (int)p.stage_bytes + 16 * p.stages + 128 + p.nw * 2 * CS_WPX * 3 * ob;
     // bands: an even number of rows, sized so that the CTAs fill a whole number of waves of resident CTAs
-    const int occ = K <= 5 ? 3 : 2;
+    const int occ = K <= 5 ? CS_MINB5 : 3;
     const long long slots = (long long)sm_count * occ;
     int best_rows = rows, best_score = 1 << 30;
     for (int wv = 1; wv <= 64; ++wv) {
@@ -99,6 +105,7 @@ bool launch_conv_sep(const uint8_t *in, size_t in_pitch, int rows, int cols, int
         const int score = br > 96 ? br - 96 : 96 - br;
         if (score < best_score) { best_score = score; best_rows = br; }
     }
+    if (const char *e = getenv("OMPIMG_CONV_BAND")) best_rows = max(2, atoi(e));
     best_rows += best_rows & 1;
     p.band_rows = best_rows;
     const int nbands = (rows + p.band_rows - 1) / p.band_rows;

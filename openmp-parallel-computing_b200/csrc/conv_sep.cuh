@@ -7,8 +7,10 @@
 // streams the band's input rows (two per stage) into a shared-memory ring with 1-D bulk asynchronous
 // copies (cp.async.bulk -> UBLKCP, mbarrier completion); rows need only 4-byte alignment (the copy
 // starts at the 16-byte boundary below the row, the consumers add the row's misalignment).  Each
-// consumer lane owns 4 pixels (12 output bytes) and walks down the band; output rows leave through a
-// per-warp staging buffer and bulk shared->global copies, so HBM sees full lines in both directions.
+// consumer lane owns 4 pixels (12 output bytes) and walks down the band; output rows are transposed
+// through a per-warp staging buffer so that the warp stores full 16-byte pieces of contiguous rows.
+// The ring has a multiple of (K+1)/2 stages, so the stage of an unrolled trip is a compile-time
+// offset (no wrap test per trip).
 //
 // Arithmetic per lane and input row (K = 5: 8 input pixels, K = 9: 12):
 //   1. de-interleave: 2 PRMT per planar word (r0 r1 r2 r3), (g0..g3), (b0..b3)  -- this removes the
@@ -34,7 +36,13 @@
 
 namespace ompimg {
 
-constexpr int CS_NW = 8;                 // consumer warps per CTA
+#ifndef CS_MINB5
+#define CS_MINB5 4                     // resident CTAs per SM the K <= 5 kernels are compiled for (K > 5: 3)
+#endif
+#ifndef CS_NWARPS
+#define CS_NWARPS 4
+#endif
+constexpr int CS_NW = CS_NWARPS;         // consumer warps per CTA
 constexpr int CS_LPX = 4;                // output pixels per lane
 constexpr int CS_WPX = 32 * CS_LPX;      // output pixels per warp and row
 
@@ -46,9 +54,10 @@ struct ConvSepParams {
     int rows, cols;
     int band_rows;               // even
     int nw, stages;
+    int relaxed;                 // producer sleeps between probes of the empty barrier
     uint32_t row_slot, stage_bytes;
     uint32_t in_row_bytes;       // (cols+K-1)*3
-    uint32_t out_bulk;           // output rows are 16-byte aligned: bulk stores
+    uint32_t out_wide;           // output rows are 16-byte aligned: 128-bit stores through the staging buffer
     uint32_t th[4][3];           // horizontal tap words
     uint32_t ut[5];              // vertical tap-pair words: bytes (u[2q], u[2q+1], u[2q-1], u[2q])
     uint32_t magic;
@@ -93,7 +102,7 @@ __device__ __forceinline__ uint32_t dp2(uint32_t a, uint32_t b, uint32_t c) {
 // DIV: 0 acc >> shift | 1 umulhi(acc, magic) | 2 acc / norm (signed) | 3 byte 1 (norm 256, u8 out) | 4 byte 2 (norm 65536, u8 out)
 // VBOX (DIV 0 or 1 only): see the header comment.
 template <int K, bool OUT_U8, int DIV, bool VBOX>
-__global__ void __launch_bounds__((CS_NW + 1) * 32, K <= 5 ? 3 : 2) conv_sep_kernel(const __grid_constant__ ConvSepParams p) {
+__global__ void __launch_bounds__((CS_NW + 1) * 32, K <= 5 ? CS_MINB5 : 3) conv_sep_kernel(const __grid_constant__ ConvSepParams p) {
     constexpr bool SG = DIV == 2;
     constexpr int NP = (K + 1) / 2;                 // trips per unrolled body; pair-rows in the vertical window
     constexpr int NPX = CS_LPX + K - 1;             // input pixels per lane
@@ -130,7 +139,7 @@ __global__ void __launch_bounds__((CS_NW + 1) * 32, K <= 5 ? 3 : 2) conv_sep_ker
         int s = 0;
         uint32_t ph = 0;
         for (int t = 0; t < ntrips; ++t) {
-            if (t >= S) mbar_wait_relaxed(empty0 + 8 * s, ph ^ 1);
+            if (t >= S) { if (p.relaxed) mbar_wait_relaxed(empty0 + 8 * s, ph ^ 1); else mbar_wait(empty0 + 8 * s, ph ^ 1); }
             const uint32_t d0 = smem0 + s * p.stage_bytes;
             // a dummy row (odd row count) re-sends the row before it
             const uint8_t *g1 = r + 1 <= rlast ? gs + p.in_pitch : gs;
@@ -159,16 +168,20 @@ __global__ void __launch_bounds__((CS_NW + 1) * 32, K <= 5 ? 3 : 2) conv_sep_ker
     // ---------------------------------------------------------------------- consumer warps
     const int seg0 = (xs + warp * CS_WPX) * 3;                                  // first output byte column of the warp
     const int nval = max(0, min(CS_WPX * 3, p.cols * 3 - seg0));                 // valid output byte columns of the warp
-    const bool bulk = p.out_bulk && nval == CS_WPX * 3;
+    const bool wide = p.out_wide && nval == CS_WPX * 3;
     const int lval = nval - lane * 12;                                          // valid output values of the lane (<= 0: none)
     const uint32_t my = keep(smem0 + (uint32_t)(warp * CS_WPX + lane * CS_LPX) * 3u);
     const uint32_t row_slot = keep(p.row_slot);
     const uint32_t stage_bytes = keep(p.stage_bytes);
-    const uint32_t ring_bytes = keep((uint32_t)S * p.stage_bytes);
-    const uint32_t eoff = keep(8u * (uint32_t)S);
+    const uint32_t ring_bytes = (uint32_t)S * p.stage_bytes;
+    const uint32_t eoff = 8u * (uint32_t)S;
     const uint32_t pitch_lo = keep((uint32_t)p.in_pitch);
-    const uint32_t stg_warp = staging0 + (uint32_t)warp * (4u * WROW);
-    const uint32_t stg = keep(stg_warp + (uint32_t)lane * (12u * OB));
+    // staging: two output rows per warp; written as 12 values per lane, read back as 16-byte pieces
+    // (piece c = lane + 32*j lies in row c / PPR at byte (c % PPR) * 16; j < NPC)
+    constexpr int PPR = (int)WROW / 16, NPC = 2 * PPR / 32 + (2 * PPR % 32 ? 1 : 0);
+    const uint32_t stg_warp = staging0 + (uint32_t)warp * (2u * WROW);
+    const uint32_t stg = stg_warp + (uint32_t)lane * (12u * OB);
+    const uint32_t stg_rd = stg_warp + (uint32_t)lane * 16u;
     uint32_t mrow = (uint32_t)(uintptr_t)p.in + (uint32_t)ya * pitch_lo;        // low address bits of the current input row
     uint8_t *orow = p.out + (size_t)ya * p.out_pitch + (size_t)seg0 * OB;       // next output row of this warp
     int ro = ya;
@@ -180,24 +193,23 @@ __global__ void __launch_bounds__((CS_NW + 1) * 32, K <= 5 ? 3 : 2) conv_sep_ker
 #pragma unroll
     for (int q = 0; q < 6; ++q) SUM[q] = 0u;
 
-    uint32_t so = 0, fb = full0, ph = 0, sbuf = 0;
+    uint32_t so = 0, fb = full0, ph = 0;           // ring position of the unrolled body's first trip
     for (int t0 = 0; t0 < ntrips; t0 += NP) {
 #pragma unroll
         for (int s = 0; s < NP; ++s) {
             const int t = t0 + s;
             if (t < ntrips) {
-                mbar_wait(fb, ph);
+                mbar_wait(fb + 8 * s, ph);
                 uint32_t w[2][NWRD];
 #pragma unroll
                 for (int rho = 0; rho < 2; ++rho) {
-                    const uint32_t a = my + so + (uint32_t)rho * row_slot + (mrow & 15u);
+                    const uint32_t a = my + so + (uint32_t)s * stage_bytes + (uint32_t)rho * row_slot + (mrow & 15u);
                     mrow += pitch_lo;
 #pragma unroll
                     for (int i = 0; i < NWRD; ++i) w[rho][i] = lds32(a + 4 * i);
                 }
-                bulk_wait_read<1>();                           // (elected lane) the staging buffer of two trips ago has left
-                __syncwarp();
-                if (elect_one()) mbar_arrive(fb + eoff);       // both rows of the stage are in registers
+                __syncwarp();                                  // also: every lane has read the previous trip's staging rows
+                if (elect_one()) mbar_arrive(fb + 8 * s + eoff);   // both rows of the stage are in registers
 
                 const bool emit = t >= (K - 1) / 2;
                 const bool two = ro + 1 < yb;
@@ -291,8 +303,8 @@ __global__ void __launch_bounds__((CS_NW + 1) * 32, K <= 5 ? 3 : 2) conv_sep_ker
 #pragma unroll
                             for (int k = 0; k < 3; ++k)
                                 o[k] = prmt(prmt(Y[CS_COL(4 * k)], Y[CS_COL(4 * k + 1)], SEL), prmt(Y[CS_COL(4 * k + 2)], Y[CS_COL(4 * k + 3)], SEL), 0x5410);
-                            if (bulk) {
-                                const uint32_t d = stg + (sbuf * 2u + half) * WROW;
+                            if (wide) {
+                                const uint32_t d = stg + half * WROW;
                                 sts32(d, o[0]); sts32(d + 4, o[1]); sts32(d + 8, o[2]);
                             } else if (lval > 0 && live) {
                                 uint8_t *gp = grow + lane * 12;
@@ -307,8 +319,8 @@ __global__ void __launch_bounds__((CS_NW + 1) * 32, K <= 5 ? 3 : 2) conv_sep_ker
                                 }
                             }
                         } else {
-                            if (bulk) {
-                                const uint32_t d = stg + (sbuf * 2u + half) * WROW;
+                            if (wide) {
+                                const uint32_t d = stg + half * WROW;
 #pragma unroll
                                 for (int k = 0; k < 3; ++k)
                                     sts128(d + 16 * k, make_uint4(Y[CS_COL(4 * k)], Y[CS_COL(4 * k + 1)], Y[CS_COL(4 * k + 2)], Y[CS_COL(4 * k + 3)]));
@@ -323,27 +335,27 @@ __global__ void __launch_bounds__((CS_NW + 1) * 32, K <= 5 ? 3 : 2) conv_sep_ker
                 }
 #undef CS_COL
                 if (emit) {
-                    if (bulk) {
-                        fence_async_smem();
+                    if (wide) {
                         __syncwarp();
-                        if (elect_one()) {
-                            const uint32_t d = stg_warp + sbuf * 2u * WROW;
-                            bulk_s2g(orow, d, WROW);
-                            if (two) bulk_s2g(orow + p.out_pitch, d + WROW, WROW);
+#pragma unroll
+                        for (int j = 0; j < NPC; ++j) {
+                            const int c = lane + 32 * j;
+                            if (2 * PPR % 32 == 0 || j + 1 < NPC || c < 2 * PPR) {
+                                const int row = c >= PPR;
+                                if (row == 0 || two)
+                                    *reinterpret_cast<uint4 *>(orow + (row ? p.out_pitch : 0) + (size_t)(c - row * PPR) * 16) = lds128(stg_rd + 512u * j);
+                            }
                         }
-                        bulk_commit();
-                        sbuf ^= 1u;
                     }
                     orow += 2 * p.out_pitch;
                     ro += 2;
                 }
-                so += stage_bytes;
-                fb += 8;
-                if (so == ring_bytes) { so = 0; fb = full0; ph ^= 1; }
             }
         }
+        so += NP * stage_bytes;
+        fb += 8 * NP;
+        if (so == ring_bytes) { so = 0; fb = full0; ph ^= 1; }
     }
-    bulk_wait_all<0>();
 }
 
 template <int K>

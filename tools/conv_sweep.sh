@@ -1,0 +1,8 @@
+for k in conv5 conv9 conv5g conv9g; do
+ for st in 4 6 8; do for rl in 1 0; do
+  echo -n "stages=$st relax=$rl "; OMPIMG_CONV_STAGES=$st OMPIMG_CONV_RELAX=$rl python tools/prof.py $k --iters 20 2>&1 | tail -1
+ done; done
+ for band in 38 56 112 148; do
+  echo -n "band=$band "; OMPIMG_CONV_BAND=$band python tools/prof.py $k --iters 20 2>&1 | tail -1
+ done
+done

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """tools/prof.py -- launch one kernel of the path a few times on a working set larger than L2, for ncu.
 
-    python tools/prof.py fused|sobel|gray|pass|conv5|conv9|sums [--frames N] [--iters K]
+    python tools/prof.py fused|sobel|gray|pass|conv5|conv9|conv5g|conv9g|sums [--frames N] [--iters K]
 
 Prints the CUDA-event time per launch (never quote a number taken under a profiler).
 """
@@ -49,15 +49,21 @@ def main():
         pkg.synth_dev(src, src.nbytes, 3); dst.fill(0)
         fn = lambda: L.ompimg_gray_sobel_pass_dev(src.ptr, W * 3, 3, dst.ptr, W, W, H, n, px * 3, px, 0)
         bpp = 6
-    elif a.kernel in ("conv5", "conv9"):
-        K = int(a.kernel[4:])
+    elif a.kernel in ("conv5", "conv9", "conv5g", "conv9g"):
+        K = int(a.kernel[4])
         rows = cols = 8192
         n, px = 1, rows * cols
         pr, pc = rows + K - 1, cols + K - 1
         src, dst = pkg.DeviceBuffer(pr * pc * 3), pkg.DeviceBuffer(rows * cols * 3)
         pkg.synth_dev(src, src.nbytes, 4)
         taps = np.ones(K * K, np.int32)
-        fn = lambda: L.ompimg_conv_u8_dev(src.ptr, pc * 3, rows, cols, K, taps.ctypes.data, K * K, dst.ptr, cols * 3, 0)
+        if a.kernel.endswith("g"):                      # binomial taps
+            b = np.array([1.0])
+            for _ in range(K - 1):
+                b = np.convolve(b, [1, 1])
+            taps = np.ascontiguousarray(np.outer(b, b).reshape(-1), np.int32)
+        norm = int(taps.sum())
+        fn = lambda: L.ompimg_conv_u8_dev(src.ptr, pc * 3, rows, cols, K, taps.ctypes.data, norm, dst.ptr, cols * 3, 0)
         bpp = 6
     elif a.kernel == "sums":
         rows = cols = 8192
