@@ -418,39 +418,99 @@ cudaError_t launch_gray_avg3(const uint8_t *rgb, size_t in_pitch, uint8_t *out, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// a7: channel sums (old/parallel_avg_pixel.c:17-30).  Pure read stream: 48-byte groups per lane,
-// per-lane 32-bit partials flushed to 64-bit, one atomicAdd triple per warp.
+// a7: channel sums (old/parallel_avg_pixel.c:17-30).  Pure read stream, 3 B/px.
+//
+// A "line" is a run of whole pixels that starts 16-byte aligned (the whole image when rows are
+// dense, else one row).  A warp reads tiles of 96 consecutive 16-byte pieces with three fully
+// coalesced 128-bit loads (lane t takes pieces t, t+32, t+64 of the tile).  Piece j of a line
+// starts at byte 16j, i.e. at channel phase j mod 3 -- and (t + 32k) mod 3 does not depend on the
+// tile, so a lane simply adds up the bytes of each piece by byte position mod 3 (12 dp4a against
+// constant masks, no shuffling of bytes) into 3x3 accumulators and rotates them to channels once,
+// at the end.  Two tiles are in flight per warp iteration.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) channel_sums_kernel(const uint8_t *rgb, size_t pitch, int rows, int cols, unsigned long long *sums) {
-    unsigned long long s0 = 0, s1 = 0, s2 = 0;
-    const bool vec = (((uintptr_t)rgb & 15) == 0) && (pitch % 16 == 0);
-    const long long gpr = vec ? cols / 16 : 0;                 // full 16-px groups per row
-    const long long ngroups = gpr * rows;
-    const uint32_t ONES = 0x01010101u;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ngroups; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / gpr, g = i - r * gpr;
-        const uint4 *src = reinterpret_cast<const uint4 *>(rgb + r * pitch + g * 48);
-        const uint4 A = __ldg(src), B = __ldg(src + 1), C = __ldg(src + 2);
-        const uint32_t w[12] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, C.x, C.y, C.z, C.w};
-        uint32_t a0 = 0, a1 = 0, a2 = 0;
+__device__ __forceinline__ uint32_t dp4a_uu(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// sums of the bytes at positions = 0, 1, 2 (mod 3) of a 16-byte piece
+__device__ __forceinline__ void piece_sums(const uint4 v, uint32_t (&a)[3]) {
+    // byte position of word w, byte b is 4w+b: class (4w+b) mod 3 = (w+b) mod 3
+    a[0] = dp4a_uu(v.x, 0x01000001u, a[0]); a[1] = dp4a_uu(v.x, 0x00000100u, a[1]); a[2] = dp4a_uu(v.x, 0x00010000u, a[2]);
+    a[1] = dp4a_uu(v.y, 0x01000001u, a[1]); a[2] = dp4a_uu(v.y, 0x00000100u, a[2]); a[0] = dp4a_uu(v.y, 0x00010000u, a[0]);
+    a[2] = dp4a_uu(v.z, 0x01000001u, a[2]); a[0] = dp4a_uu(v.z, 0x00000100u, a[0]); a[1] = dp4a_uu(v.z, 0x00010000u, a[1]);
+    a[0] = dp4a_uu(v.w, 0x01000001u, a[0]); a[1] = dp4a_uu(v.w, 0x00000100u, a[1]); a[2] = dp4a_uu(v.w, 0x00010000u, a[2]);
+}
+
+__global__ void __launch_bounds__(256) channel_sums_kernel(const uint8_t *rgb, size_t line_pitch, long long nlines, long long line_bytes,
+                                                           unsigned long long *sums) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long pieces = line_bytes >> 4;                    // whole 16-byte pieces per line
+    const long long tiles = (pieces + 95) / 96;
+    uint32_t acc[3][3];                                          // [k: which of the lane's three pieces][byte position mod 3]
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            // bytes: (r g b r)(g b r g)(b r g b): gather the four r's, g's, b's of 4 pixels, then dp4a with ones
-            const uint32_t a = w[3 * q], b = w[3 * q + 1], c = w[3 * q + 2];
-            const uint32_t rr = prmt(prmt(a, b, 0x0630), c, 0x5210);   // r0 r1 r2 | r3
-            const uint32_t gg = prmt(prmt(a, b, 0x0741), c, 0x6210);
-            const uint32_t bb = prmt(prmt(a, b, 0x0052), c, 0x7410);
-            a0 = __dp4a(rr, ONES, a0);
-            a1 = __dp4a(gg, ONES, a1);
-            a2 = __dp4a(bb, ONES, a2);
+    for (int k = 0; k < 3; ++k) acc[k][0] = acc[k][1] = acc[k][2] = 0u;
+    unsigned long long s[3] = {0, 0, 0};                         // channel sums of this thread
+    const uint4 Z = make_uint4(0u, 0u, 0u, 0u);
+    for (long long line = blockIdx.y; line < nlines; line += gridDim.y) {
+        const uint4 *base = reinterpret_cast<const uint4 *>(rgb + line * line_pitch);
+        const long long tstep = (long long)gridDim.x * 8;
+        for (long long t = (long long)blockIdx.x * 8 + warp; t < tiles; t += 2 * tstep) {
+            const long long j0 = t * 96 + lane, j1 = j0 + tstep * 96;
+            uint4 v[6];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                v[k] = j0 + 32 * k < pieces ? __ldg(base + j0 + 32 * k) : Z;
+                v[3 + k] = j1 + 32 * k < pieces ? __ldg(base + j1 + 32 * k) : Z;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { piece_sums(v[k], acc[k]); piece_sums(v[3 + k], acc[k]); }
         }
-        s0 += a0; s1 += a1; s2 += a2;
+        // the < 16 bytes after the last whole piece of the line
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            const uint8_t *q = rgb + line * line_pitch;
+            for (long long i = pieces << 4; i < line_bytes; ++i) {
+                const int c = (int)(i % 3);
+                s[0] += c == 0 ? q[i] : 0; s[1] += c == 1 ? q[i] : 0; s[2] += c == 2 ? q[i] : 0;
+            }
+        }
     }
-    // remaining pixels (row tails, or everything when the layout is not 16-byte friendly)
-    const long long tail0 = gpr * 16, tpr = cols - tail0;
-    const long long nt = tpr * rows;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / tpr, x = tail0 + (i - r * tpr);
+    // piece k of lane t sits at channel phase (t + 32k) mod 3: byte position class c holds channel (c + phase) mod 3
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int phase = (lane + 2 * k) % 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int ch = (c + phase) % 3;
+            s[0] += ch == 0 ? acc[k][c] : 0u;
+            s[1] += ch == 1 ? acc[k][c] : 0u;
+            s[2] += ch == 2 ? acc[k][c] : 0u;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s[0] += __shfl_xor_sync(0xffffffffu, s[0], o);
+        s[1] += __shfl_xor_sync(0xffffffffu, s[1], o);
+        s[2] += __shfl_xor_sync(0xffffffffu, s[2], o);
+    }
+    // one atomic triple per CTA: thousands of same-address atomics from every warp cost more than the read itself
+    __shared__ unsigned long long part[8][3];
+    if (lane == 0) { part[warp][0] = s[0]; part[warp][1] = s[1]; part[warp][2] = s[2]; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        unsigned long long tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += part[w][threadIdx.x];
+        atomicAdd(sums + threadIdx.x, tot);
+    }
+}
+
+// any alignment / pitch: one thread per pixel
+__global__ void __launch_bounds__(256) channel_sums_generic_kernel(const uint8_t *rgb, size_t pitch, int rows, int cols, unsigned long long *sums) {
+    unsigned long long s0 = 0, s1 = 0, s2 = 0;
+    const long long total = (long long)rows * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cols, x = i - r * cols;
         const uint8_t *px = rgb + r * pitch + x * 3;
         s0 += px[0]; s1 += px[1]; s2 += px[2];
     }
@@ -460,16 +520,30 @@ __global__ void __launch_bounds__(256) channel_sums_kernel(const uint8_t *rgb, s
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(sums, s0); atomicAdd(sums + 1, s1); atomicAdd(sums + 2, s2);
-    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(sums, s0); atomicAdd(sums + 1, s1); atomicAdd(sums + 2, s2); }
 }
 
 cudaError_t launch_channel_sums(const uint8_t *rgb, size_t pitch, int rows, int cols, unsigned long long *sums_dev, int sm_count, cudaStream_t st) {
-    const long long groups = (long long)rows * ((cols + 15) / 16);
-    const int grid = (int)max(1LL, min((groups + 255) / 256, (long long)sm_count * 8));
+    const size_t row_bytes = (size_t)cols * 3;
+    const bool dense = pitch == row_bytes || rows == 1;
     count_launch();
-    channel_sums_kernel<<<grid, 256, 0, st>>>(rgb, pitch, rows, cols, sums_dev);
+    if (((uintptr_t)rgb & 15) == 0 && (dense || (pitch & 15) == 0)) {
+        const long long nlines = dense ? 1 : rows;
+        const long long line_bytes = dense ? (long long)row_bytes * rows : (long long)row_bytes;
+        // accumulators are 32-bit: 6 * 255 per piece, a lane sees line_bytes / (16 * 32 * 8 * grid.x) pieces per k
+        const long long tiles = (line_bytes / 16 + 95) / 96;
+        const long long gx = max(1LL, min((tiles + 15) / 16, dense ? (long long)sm_count * 8 : 64LL));
+        const long long gy = max(1LL, min(nlines, ((long long)sm_count * 8 + gx - 1) / gx));
+        // worst case per 32-bit accumulator: pieces per lane and k over the whole launch
+        const double per_lane = (double)line_bytes / 16.0 / 96.0 / (double)(gx * 8) * (double)((nlines + gy - 1) / gy) + 2.0;
+        if (per_lane * 6.0 * 255.0 < 4.0e9) {
+            channel_sums_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, st>>>(rgb, pitch, nlines, line_bytes, sums_dev);
+            return cudaGetLastError();
+        }
+    }
+    const long long total = (long long)rows * cols;
+    const int grid = (int)max(1LL, min((total + 255) / 256, (long long)sm_count * 16));
+    channel_sums_generic_kernel<<<grid, 256, 0, st>>>(rgb, pitch, rows, cols, sums_dev);
     return cudaGetLastError();
 }
 

@@ -483,6 +483,32 @@ def test_separable_convolution_device_layouts(gpu, O, K, kind):
         src.free()
 
 
+
+def test_channel_sums_device_layouts(gpu, O):
+    """a7 through the device entry point: dense and pitched rows, aligned and unaligned bases, rows whose byte
+    count is not a multiple of 16 or of the 1536-byte tile (old/parallel_avg_pixel.c:17-30 sums)."""
+    L = gpu.lib()
+    #        rows cols  pitch_pad base_off
+    cases = [(1, 1, 0, 0), (3, 5, 0, 0), (17, 512, 0, 0), (9, 515, 13, 0), (40, 1001, 0, 0), (25, 2048, 16, 0), (31, 700, 4, 0),
+             (12, 333, 3, 16), (12, 333, 0, 5), (64, 4096, 128, 0), (2, 70000, 0, 0)]
+    for (rows, cols, pad, off) in cases:
+        img = O.synth(rows * cols * 3, 0xA7 + rows * cols).reshape(rows, cols * 3)
+        pitch = cols * 3 + pad
+        if pad and pad % 16 == 0:
+            pitch = (cols * 3 + 15) // 16 * 16 + pad
+        buf = gpu.DeviceBuffer(off + pitch * rows + 64)
+        buf.fill(0xFF)
+        assert L.ompimg_copy2d_h2d(buf.ptr + off, pitch, img.ctypes.data, cols * 3, cols * 3, rows, 0) == 0
+        sums = gpu.DeviceBuffer(64)
+        sums.fill(0)
+        ck(gpu, L.ompimg_channel_sums_dev(buf.ptr + off, pitch, rows, cols, sums.ptr, 0))
+        gpu.sync(0)
+        got = sums.download(24).view(np.uint64)
+        want = img.reshape(rows, cols, 3).astype(np.uint64).sum(axis=(0, 1))
+        assert got.tolist() == want.tolist(), (rows, cols, pad, off)
+        buf.free(); sums.free()
+
+
 def test_avg_and_gray3_accumulate_and_ragged(gpu, O):
     for (rows, cols) in [(1, 1), (7, 5), (33, 100), (240, 1001), (1080, 1920)]:
         img = O.synth(rows * cols * 3, rows + cols).reshape(rows, cols, 3)

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
+    ap.add_argument("--rows", type=int, default=8192, help="rows of the square-ish cfg4 image (sums)")
     a = ap.parse_args()
     pkg = importlib.import_module("openmp-parallel-computing_b200")
     pkg.init(0)
@@ -66,7 +67,7 @@ def main():
         fn = lambda: L.ompimg_conv_u8_dev(src.ptr, pc * 3, rows, cols, K, taps.ctypes.data, norm, dst.ptr, cols * 3, 0)
         bpp = 6
     elif a.kernel == "sums":
-        rows = cols = 8192
+        rows, cols = a.rows, 8192
         n, px = 1, rows * cols
         src, dst = pkg.DeviceBuffer(px * 3), pkg.DeviceBuffer(64)
         pkg.synth_dev(src, src.nbytes, 5); dst.fill(0)
