@@ -151,7 +151,7 @@ def ncu_traffic():
     p = ROOT / "profiles" / "traffic.json"
     if p.exists():
         try:
-            return json.loads(p.read_text()).get("sobel_rows_kernel<3,0>")
+            return json.loads(p.read_text()).get("sobel_warp_kernel<3,0>")
         except Exception:
             return None
     return None
@@ -290,7 +290,7 @@ def run_ours(args, dist: Dist):
     peak, peak_src = measured_peak()
     kernel_ms = ms / args.steps                               # this rank's launches: one per step
     achieved = BYTES_PER_PX * nf * PX / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "sobel_rows_kernel<3,0> (fused RGB->luma->Sobel)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "sobel_warp_kernel<3,0> (fused RGB->luma->Sobel, warp-autonomous bulk-copy rings)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic(),
                 "algorithmic_bytes_per_launch": BYTES_PER_PX * nf * PX, "frac_of_nominal_8TBs": achieved / 8000.0}
 

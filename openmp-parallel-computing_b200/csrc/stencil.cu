@@ -243,6 +243,264 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32, CH == 1 ? 3 : 2) sobel_r
 }
 
 // ---------------------------------------------------------------------------------------------
+// Warp-autonomous variant (no halo rows from peers): every warp is its own pipeline.
+//
+// A warp owns a 512-pixel column strip of a band of rows and runs a private ring of stages (three
+// rows each) with a private mbarrier per stage; an elected lane issues the strip's bulk copies
+// (512*CH + 2x16 bytes per row) and the whole warp consumes them -- there is no producer warp, no
+// empty barrier and no coupling between the warps of a CTA, so a warp never waits for a slower
+// neighbour before its next rows can be requested (in sobel_rows_kernel the ring is refilled only
+// when all eight warps have released a stage, and the consumers measured ~20 % of their time in
+// that wait).  The CTA is 8 warps = 256 threads, so three CTAs per SM get 80 registers instead of
+// 72 (288 threads), which removes the spills of the plane kernel.  Same arithmetic, same results.
+// ---------------------------------------------------------------------------------------------
+struct WarpStencilParams {
+    const uint8_t *src;
+    uint8_t *dst;
+    size_t src_pitch, dst_pitch, src_stride, dst_stride;
+    int width, height;
+    int nbands, rows_per_band, nstrips;
+    int fold;               // the last strip is at most 256 pixels wide: one warp takes it for TWO bands (16 lanes each)
+    int tasks_per_frame;
+    long long ntasks;       // nframes * tasks_per_frame, one task per warp
+    uint32_t row_bytes16;   // round16(width*CH)
+};
+constexpr int WS_WARPS = 8;
+template <int CH> constexpr int ws_stages() { return CH == 1 ? 4 : 2; }
+template <int CH> constexpr int ws_half_slot() { return 32 + 256 * CH; }          // half a strip and its two 16-byte halo blocks
+template <int CH> constexpr int ws_row_slot() { return 2 * ws_half_slot<CH>(); }
+template <int CH> constexpr int ws_smem() { return WS_WARPS * (ws_stages<CH>() * 3 * ws_row_slot<CH>() + 8 * ws_stages<CH>() + 48) + 128; }
+
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+
+// rows a band consumes / produces (band 0 takes one output row more, see sobel_rows_kernel)
+__device__ __forceinline__ void ws_band_rows(const WarpStencilParams &p, int band, int &rin0, int &rin1) {
+    const int ya = band == 0 ? 0 : band * p.rows_per_band + 1, yb = min(p.height, (band + 1) * p.rows_per_band + 1);
+    rin0 = max(ya - 1, 0);
+    rin1 = band < p.nbands ? min(yb, p.height - 1) : rin0 - 1;      // a band that does not exist consumes nothing
+}
+
+template <int CH, int FMA_MODE, bool BIAS>
+__global__ void __launch_bounds__(WS_WARPS * 32, CH == 1 ? 3 : 2) sobel_warp_kernel(const __grid_constant__ WarpStencilParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int BPP = CH, S = ws_stages<CH>();
+    constexpr uint32_t HALF_SLOT = ws_half_slot<CH>(), ROW_SLOT = ws_row_slot<CH>(), STAGE = 3 * ROW_SLOT;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long task = (long long)blockIdx.x * WS_WARPS + warp;
+    if (task >= p.ntasks) return;                       // warps are independent: no CTA-wide barrier below
+    const long long frame = task / p.tasks_per_frame;
+    const int tf = (int)(task - frame * p.tasks_per_frame);
+    // full strips first (strip-major inside a band, so that the warps of a CTA read one contiguous row piece),
+    // then the folded tasks: the narrow last strip of bands 2i and 2i+1 in the two halves of one warp
+    const int nfull = p.fold ? p.nstrips - 1 : p.nstrips;
+    const bool folded = tf >= p.nbands * nfull;
+    const int strip = folded ? p.nstrips - 1 : tf % nfull;
+    const int band_a = folded ? 2 * (tf - p.nbands * nfull) : tf / nfull;
+    const int hb = folded ? lane >> 4 : 0;              // which half of the warp (folded tasks)
+    const int lc = folded ? lane & 15 : lane;           // 16-pixel group of the lane inside its (half) strip
+    const uint32_t ring0 = (smem_u32(smem) + 127u & ~127u) + (uint32_t)warp * (S * STAGE);
+    const uint32_t bar0 = (smem_u32(smem) + 127u & ~127u) + WS_WARPS * (S * STAGE) + (uint32_t)warp * (8 * S);
+    const uint32_t scr0 = (smem_u32(smem) + 127u & ~127u) + WS_WARPS * (S * STAGE + 8 * S) + (uint32_t)warp * 48u;   // see request()
+
+    const int xs = strip * 512;
+    const uint8_t *src = p.src + (size_t)frame * p.src_stride;
+    uint8_t *dst = p.dst + (size_t)frame * p.dst_stride;
+    int a0, a1, b0, b1;                                 // source rows of the two halves' bands (half B only in folded tasks)
+    ws_band_rows(p, band_a, a0, a1);
+    ws_band_rows(p, folded ? band_a + 1 : p.nbands, b0, b1);
+    const int nin_a = a1 - a0 + 1, nin_b = b1 - b0 + 1;
+    const int nin_max = max(nin_a, nin_b);
+    if (nin_max < 3) return;
+    const int ntrips = (nin_max + 2) / 3;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) mbar_init(bar0 + 8 * s, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    // What the elected lane needs to request rows lives in the warp's scratch words, not in registers of
+    // all 32 lanes (the kernel is register-bound): address and index of the next source row of each half,
+    // their last rows, bytes per row, stage offset of the first byte.
+    // The strip's bytes of a row are [lo, hi), 16-byte halo blocks included where they exist.
+    if (lane == 0) {
+        const uint32_t lo = xs == 0 ? 0u : (uint32_t)xs * BPP - 16u;
+        const uint32_t hi = min(p.row_bytes16, (uint32_t)(xs + (folded ? 256 : 512)) * BPP + 16u);
+        const u64 ga = (u64)(uintptr_t)(src + (size_t)a0 * p.src_pitch + lo), gb = (u64)(uintptr_t)(src + (size_t)max(b0, 0) * p.src_pitch + lo);
+        sts128(scr0, make_uint4((uint32_t)ga, (uint32_t)(ga >> 32), (uint32_t)gb, (uint32_t)(gb >> 32)));
+        sts128(scr0 + 16, make_uint4((uint32_t)a0, (uint32_t)b0, (uint32_t)a1, (uint32_t)b1));
+        sts32(scr0 + 32, hi - lo); sts32(scr0 + 36, (xs == 0 ? 16u : 0u) | (nin_b >= 3 ? 256u : 0u));
+    }
+    __syncwarp();
+    auto request = [&](int s) {       // elected lane: the next three rows of each half into stage s (past a band's last row: that row again)
+        const uint4 c0 = lds128(scr0), c1 = lds128(scr0 + 16);
+        const uint32_t bytes = lds32(scr0 + 32), fl = lds32(scr0 + 36);
+        u64 ga = pack64(c0.x, c0.y), gb = pack64(c0.z, c0.w);
+        int ra_next = (int)c1.x, rb_next = (int)c1.y;
+        const int ra1 = (int)c1.z, rb1 = (int)c1.w;
+        const bool lb = (fl & 256u) != 0;
+        const uint32_t d0 = ring0 + s * STAGE + (fl & 255u), bar = bar0 + 8 * s;
+        mbar_expect_tx(bar, (lb ? 6u : 3u) * bytes);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            bulk_g2s(d0 + j * ROW_SLOT, reinterpret_cast<const void *>((uintptr_t)ga), bytes, bar);
+            if (ra_next < ra1) { ga += p.src_pitch; ++ra_next; }
+            if (lb) {
+                bulk_g2s(d0 + j * ROW_SLOT + HALF_SLOT, reinterpret_cast<const void *>((uintptr_t)gb), bytes, bar);
+                if (rb_next < rb1) { gb += p.src_pitch; ++rb_next; }
+            }
+        }
+        uint32_t g0, g1, g2, g3;
+        unpack64(ga, g0, g1); unpack64(gb, g2, g3);
+        sts128(scr0, make_uint4(g0, g1, g2, g3));
+        sts32(scr0 + 16, (uint32_t)ra_next); sts32(scr0 + 20, (uint32_t)rb_next);
+    };
+    if (elect_one_sync()) {
+        for (int t = 0; t < S && t < ntrips; ++t) request(t);
+    }
+
+    const int rin0 = hb ? b0 : a0;
+    const int nin = hb ? nin_b : nin_a;                 // rows this lane's half really has (the loop runs nin_max rows)
+    const int x0 = xs + 16 * lc;
+    int mode = 0;         // 0 nothing to store, 1 one 16-byte store, 2 group holds x == 0, 3 group holds x == width-1, 4 both
+    if (x0 < p.width && nin >= 3) {
+        const bool l = x0 == 0, r = x0 + 16 > p.width - 1;
+        mode = l ? (r ? 4 : 2) : (r ? 3 : 1);
+    }
+    const int plast = min(16, p.width - 1 - x0);
+    const uint32_t my = ring0 + (uint32_t)hb * HALF_SLOT + 16u + (uint32_t)lc * (16u * BPP);
+    // fused path: the first lane of a (half) strip takes its left neighbour's luma from the halo block, lane 31 its right one
+    const bool first = lc == 0;
+    const int edge_off = first ? -4 : 16 * BPP;
+    const uint32_t edge_sh = first ? 8u * (4u - BPP) : 0u;
+    const uint32_t mL = first ? 0xffffffffu : 0u, mR = lane == 31 ? 0xffffffffu : 0u;
+    const size_t dpitch = p.dst_pitch;
+    uint8_t *out = dst + (size_t)rin0 * p.dst_pitch + x0;     // row of the source row being consumed; stores go one row up
+    float half = BIAS ? 0.5f : 0.0f;
+    if (BIAS) asm volatile("" : "+f"(half));
+
+    uint32_t U[3][8], V[3][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) U[0][k] = U[1][k] = U[2][k] = V[0][k] = V[1][k] = V[2][k] = 0u;
+
+    int s = 0, t = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < nin_max; i += 3, ++t) {
+        mbar_wait(bar0 + 8 * s, ph);
+#pragma unroll
+        for (int rho = 0; rho < 3; ++rho) {
+            const int ra = rho, rb = (rho + 1) % 3, rc = (rho + 2) % 3;
+            const bool emit = i + rho >= 2 && i + rho < nin;
+            const uint32_t stage = my + (uint32_t)s * STAGE + (uint32_t)rho * ROW_SLOT;
+            uint32_t P[8], Q[9];
+            if (CH == 1) {
+                const uint32_t C64 = 0x64646464u;
+                const uint4 v = lds128(stage);
+                const uint32_t lw = lds32(stage - 4), rw = lds32(stage + 16);
+                if (rho == 2) {
+                    __syncwarp();                                   // every lane holds the stage's three rows
+                    if (elect_one_sync() && t + S < ntrips) request(s);
+                }
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    P[2 * j] = prmt(w[j], C64, 0x4140);
+                    P[2 * j + 1] = prmt(w[j], C64, 0x4342);
+                    Q[2 * j + 1] = prmt(w[j], C64, 0x4241);
+                }
+                Q[0] = (prmt(lw, w[0], 0x0403) & 0x00ff00ffu) | 0x64006400u;
+#pragma unroll
+                for (int j = 1; j < 4; ++j) Q[2 * j] = prmt(P[2 * j - 1], P[2 * j], 0x5432);
+                Q[8] = (prmt(w[3], rw, 0x0403) & 0x00ff00ffu) | 0x64006400u;
+            } else {
+                uint32_t w[4 * CH];
+                load_group_words<CH>(stage, w);
+                const uint32_t ew = lds32(stage + edge_off) >> edge_sh;
+                if (rho == 2) {
+                    __syncwarp();
+                    if (elect_one_sync() && t + S < ntrips) request(s);
+                }
+                uint32_t f[16];
+                const float MAGIC = 14942208.0f;
+                if (CH == 3) luma16_rgb<FMA_MODE>(reinterpret_cast<const uint32_t(&)[12]>(w), f, MAGIC);
+                else luma16_rgba<FMA_MODE>(reinterpret_cast<const uint32_t(&)[16]>(w), f, MAGIC);
+                const uint32_t fE = luma_px<FMA_MODE>(ew, MAGIC);
+                uint32_t fL = __shfl_up_sync(0xffffffffu, f[15], 1);
+                uint32_t fR = __shfl_down_sync(0xffffffffu, f[0], 1);
+                fL = (fE & mL) | (fL & ~mL);
+                fR = (fE & mR) | (fR & ~mR);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) P[k] = prmt(f[2 * k], f[2 * k + 1], 0x6420);
+                Q[0] = prmt(fL, f[0], 0x6420);
+#pragma unroll
+                for (int k = 1; k < 8; ++k) Q[k] = prmt(f[2 * k - 1], f[2 * k], 0x6420);
+                Q[8] = prmt(f[15], fR, 0x6420);
+            }
+            uint32_t gx[8], gy[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                U[rc][k] = hsub2(Q[k + 1], Q[k]);
+                const uint32_t t1 = hfma2(P[k], 0x40004000u /*2,2*/, 0xEA00EA00u /*-3072,-3072*/);
+                V[rc][k] = hadd2(hadd2(t1, Q[k]), Q[k + 1]);
+                U[rb][k] = hadd2(U[rb][k], U[rc][k]);
+                gx[k] = hadd2(U[ra][k], U[rb][k]);
+                gy[k] = hsub2(V[ra][k], V[rc][k]);
+            }
+            if (emit && mode) {
+                const uint4 o = sobel_mag16(gx, gy, half);
+                uint8_t *q = out - dpitch;
+                if (mode == 1) *reinterpret_cast<uint4 *>(q) = o;
+                else store_edge16(q, o, mode, plast);
+            }
+            out += dpitch;
+        }
+        if (++s == S) { s = 0; ph ^= 1; }
+    }
+}
+
+template <int CH, int FMA_MODE, bool BIAS>
+static cudaError_t launch_sobel_warp_t(const StencilArgs &a, int sm_count, cudaStream_t st) {
+    WarpStencilParams p{};
+    p.src = a.src; p.dst = a.dst; p.src_pitch = a.src_pitch; p.dst_pitch = a.dst_pitch;
+    p.src_stride = a.src_stride; p.dst_stride = a.dst_stride;
+    p.width = a.width; p.height = a.height;
+    p.nstrips = (a.width + 511) / 512;
+    p.row_bytes16 = (uint32_t)(((size_t)a.width * CH + 15) & ~(size_t)15);
+    // bands of ~130 rows (1 mod 3: each band then consumes a multiple of three source rows); shorter when the launch is small
+    const long long want = (long long)sm_count * 24 * 3;
+    int rpb = 130;
+    { static int env = -1; if (env < 0) { const char *e = getenv("OMPIMG_SOBEL_BAND"); env = e ? atoi(e) : 0; } if (env > 0) rpb = env; }
+    while (rpb > 16 && (long long)a.nframes * p.nstrips * ((a.height - 1 + rpb - 1) / rpb) < want) rpb = rpb == 130 ? 64 : rpb == 64 ? 34 : 16;
+    p.rows_per_band = rpb;
+    p.nbands = max(1, (a.height - 1 + rpb - 1) / rpb);
+    // a last strip of at most 256 pixels (3840 = 7.5 strips) would leave half a warp idle: fold two bands into one warp
+    { static int env = -1; if (env < 0) { const char *e = getenv("OMPIMG_SOBEL_FOLD"); env = e ? atoi(e) : 1; }
+      p.fold = env && p.nbands >= 2 && a.width - (p.nstrips - 1) * 512 <= 256; }
+    p.tasks_per_frame = p.fold ? p.nbands * (p.nstrips - 1) + (p.nbands + 1) / 2 : p.nbands * p.nstrips;
+    p.ntasks = (long long)a.nframes * p.tasks_per_frame;
+    const long long ctas = (p.ntasks + WS_WARPS - 1) / WS_WARPS;
+    if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
+    constexpr int smem = ws_smem<CH>();
+    static unsigned long long attr_mask = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (!(attr_mask >> dev & 1ULL)) {
+        e = cudaFuncSetAttribute(sobel_warp_kernel<CH, FMA_MODE, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_mask |= 1ULL << dev;
+    }
+    count_launch();
+    sobel_warp_kernel<CH, FMA_MODE, BIAS><<<(unsigned)ctas, WS_WARPS * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // generic fallback (any alignment / pitch): one thread per output pixel
 // ---------------------------------------------------------------------------------------------
 template <int CH, int FMA_MODE>
@@ -294,6 +552,13 @@ static cudaError_t launch_sobel_t(const StencilArgs &a, int sm_count, cudaStream
         count_launch();
         sobel_generic_kernel<CH, FMA_MODE><<<grid, 256, 0, st>>>(a);
         return cudaGetLastError();
+    }
+    {
+        // warp-autonomous pipeline whenever no halo rows come from peers (OMPIMG_SOBEL_WARP=0: the row-ring kernel, for A/B runs)
+        static int warp_mode = -1;
+        if (warp_mode < 0) { const char *e = getenv("OMPIMG_SOBEL_WARP"); warp_mode = e ? atoi(e) : 1; }
+        const bool use_warp = !a.halo_above && !a.halo_below && a.height >= 3 && warp_mode != 0;
+        if (use_warp) return launch_sobel_warp_t<CH, FMA_MODE, BIAS>(a, sm_count, st);
     }
     StencilParams p{};
     p.src = a.src; p.dst = a.dst; p.src_pitch = a.src_pitch; p.dst_pitch = a.dst_pitch;
