@@ -346,13 +346,21 @@ __global__ void __launch_bounds__(WS_WARPS * 32, CH == 1 ? 3 : 2) sobel_warp_ker
         const bool lb = (fl & 256u) != 0;
         const uint32_t d0 = ring0 + s * STAGE + (fl & 255u), bar = bar0 + 8 * s;
         mbar_expect_tx(bar, (lb ? 6u : 3u) * bytes);
+        if (!lb && ra_next + 3 <= ra1) {
+            // the common case (no second half, not at the band's end): three consecutive rows
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            bulk_g2s(d0 + j * ROW_SLOT, reinterpret_cast<const void *>((uintptr_t)ga), bytes, bar);
-            if (ra_next < ra1) { ga += p.src_pitch; ++ra_next; }
-            if (lb) {
-                bulk_g2s(d0 + j * ROW_SLOT + HALF_SLOT, reinterpret_cast<const void *>((uintptr_t)gb), bytes, bar);
-                if (rb_next < rb1) { gb += p.src_pitch; ++rb_next; }
+            for (int j = 0; j < 3; ++j) bulk_g2s(d0 + j * ROW_SLOT, reinterpret_cast<const void *>((uintptr_t)(ga + j * p.src_pitch)), bytes, bar);
+            ga += 3 * p.src_pitch;
+            ra_next += 3;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                bulk_g2s(d0 + j * ROW_SLOT, reinterpret_cast<const void *>((uintptr_t)ga), bytes, bar);
+                if (ra_next < ra1) { ga += p.src_pitch; ++ra_next; }
+                if (lb) {
+                    bulk_g2s(d0 + j * ROW_SLOT + HALF_SLOT, reinterpret_cast<const void *>((uintptr_t)gb), bytes, bar);
+                    if (rb_next < rb1) { gb += p.src_pitch; ++rb_next; }
+                }
             }
         }
         uint32_t g0, g1, g2, g3;
