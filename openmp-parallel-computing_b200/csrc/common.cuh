@@ -328,7 +328,9 @@ __device__ __forceinline__ void store_partial16(uint8_t *dst, uint4 v, int first
 //   mode 2: the group holds x == 0          -> bytes 1..15
 //   mode 3: the group holds x == width-1    -> bytes 0..plast-1 (plast in 0..15)
 //   mode 4: both (image narrower than 17)   -> byte loop
-static __device__ __noinline__ void store_edge16(uint8_t *q, uint4 o, int mode, int plast) {
+// (forced inline: as a called function its ABI pinned the row state of the Sobel kernels to fixed registers and cost
+// ~20 register moves per row on the hot path -- +9-11 % when inlined, although the code itself runs for two lanes per row)
+static __device__ __forceinline__ void store_edge16(uint8_t *q, uint4 o, int mode, int plast) {
     if (mode == 2) {
         q[1] = (uint8_t)(o.x >> 8);
         *reinterpret_cast<uint16_t *>(q + 2) = (uint16_t)(o.x >> 16);
