@@ -193,6 +193,14 @@ OMPIMG_API int  ompimg_bands_rgb_to_edge(ompimg_bands *b, float *ms_max);       
 OMPIMG_API int  ompimg_bands_download_edge(ompimg_bands *b, uint8_t *edge_host);    /* dense width*height plane, border bytes untouched */
 OMPIMG_API int  ompimg_bands_checksum(ompimg_bands *b, unsigned long long *sum);    /* sum of all interior edge bytes */
 
+/* ---- persistent worker mode (the reference's services exec the CLI once per request,
+ * microservices/grayscale/app.py:24-34, event-driven/grayscale_service/app.py:54-65) -----------------
+ * With OMPIMG_WORKER=<unix socket path> in the environment the two frozen prototypes do not create a
+ * CUDA context (~3 s per fresh process): they hand the image to the process that runs
+ * ompimg_worker_serve() (lib/ompimg_worker) and read the result back.  An unreachable worker means the
+ * calling process initialises CUDA itself; there is still no CPU path.  Blocks until signalled. */
+OMPIMG_API int ompimg_worker_serve(const char *socket_path, int device);
+
 #ifdef __cplusplus
 }
 #endif

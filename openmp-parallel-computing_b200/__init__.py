@@ -112,6 +112,7 @@ _SIGS = {
     "ompimg_bands_rgb_to_edge": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "ompimg_bands_download_edge": (C.c_int, [_vp, _vp]),
     "ompimg_bands_checksum": (C.c_int, [_vp, C.POINTER(C.c_ulonglong)]),
+    "ompimg_worker_serve": (C.c_int, [C.c_char_p, C.c_int]),
 }
 
 _lib = None

@@ -14,6 +14,7 @@
 
 #include "../../include/ompimg_b200.h"
 #include "kernels.h"
+#include "worker.h"
 
 namespace ompimg {
 std::atomic<long long> g_launch_count{0};
@@ -819,10 +820,23 @@ static void die(const char *fn) {
 // monolithic/include/parallel_to_grayscale.h:4
 extern "C" void convert_to_grayscale(unsigned char *data, int width, int height, int channels) {
     if (width <= 0 || height <= 0) return;              // the reference's loop body never runs
+    if (!g.ready && data && (channels == 3 || channels == 4)) {
+        // persistent worker mode (worker.cu): OMPIMG_WORKER names the process that holds the CUDA context
+        const char *m = getenv("OMPIMG_LUMA");
+        const int mode = (m && (!strcmp(m, "fma") || !strcmp(m, "1"))) ? OMPIMG_LUMA_FMA : OMPIMG_LUMA_STRICT;
+        const int rc = worker_call_gray(data, width, height, channels, mode, g_err, sizeof g_err);
+        if (rc == 1) return;
+        if (rc < 0) die("convert_to_grayscale");
+    }
     if (ompimg_gray_inplace_host(data, width, height, channels) != OMPIMG_OK) die("convert_to_grayscale");
 }
 // monolithic/include/sobel.h:3-5
 extern "C" void sobel_edge(const unsigned char *src, unsigned char *dst, int width, int height) {
     if (width < 3 || height < 3) return;                // no interior pixels: the reference writes nothing
+    if (!g.ready && src && dst) {
+        const int rc = worker_call_sobel(src, dst, width, height, g_err, sizeof g_err);
+        if (rc == 1) return;
+        if (rc < 0) die("sobel_edge");
+    }
     if (ompimg_sobel_host(src, dst, width, height) != OMPIMG_OK) die("sobel_edge");
 }

@@ -1,0 +1,214 @@
+"""Persistent worker mode (csrc/worker.cu).
+
+CPU tests: the CLIENT side of the frozen prototypes -- with OMPIMG_WORKER set they must not touch CUDA at all, so
+it can be exercised here without a GPU against a fake worker that speaks the wire format and answers with the
+oracle's results (the oracle is the checker, never the product).  GPU tests: the real `ompimg_worker` process
+serving the reference's unmodified CLI drivers.
+"""
+import hashlib
+import os
+import socket
+import struct
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from common import ROOT, sha
+
+REQ = struct.Struct("<IIiiiiQ")          # magic, op, width, height, channels, luma_mode, nbytes
+REP = struct.Struct("<IiQ232s")          # magic, status, nbytes, msg
+MAGIC = 0x4F4D5042
+LIB = ROOT / "openmp-parallel-computing_b200" / "lib" / "libompimg_b200.so"
+WORKER = ROOT / "openmp-parallel-computing_b200" / "lib" / "ompimg_worker"
+
+CLIENT = r"""
+import ctypes as C, hashlib, sys, numpy as np
+L = C.CDLL(sys.argv[1])
+h, w, ch = 37, 53, int(sys.argv[2])
+rng = np.random.default_rng(5)
+img = rng.integers(0, 256, (h, w, ch), dtype=np.uint8)
+for _ in range(int(sys.argv[3])):
+    L.convert_to_grayscale(C.c_void_p(img.ctypes.data), w, h, ch)
+plane = np.ascontiguousarray(img[:, :, 0])
+dst = np.full((h, w), 0xAB, np.uint8)
+L.sobel_edge(C.c_void_p(plane.ctypes.data), C.c_void_p(dst.ctypes.data), w, h)
+print(hashlib.sha256(img.tobytes()).hexdigest(), hashlib.sha256(dst.tobytes()).hexdigest(), L.ompimg_launch_count())
+"""
+
+
+def recv_full(c, n):
+    buf = bytearray()
+    while len(buf) < n:
+        part = c.recv(n - len(buf))
+        if not part:
+            return None
+        buf += part
+    return bytes(buf)
+
+
+class FakeWorker:
+    """Speaks worker.cu's wire format; computes with the oracle.  `fail_op` makes that op answer with an error."""
+
+    def __init__(self, O, path, fail_op=None):
+        self.O, self.path, self.fail_op = O, str(path), fail_op
+        self.requests = []
+        self.srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        self.srv.bind(self.path)
+        self.srv.listen(8)
+        self.thread = threading.Thread(target=self.run, daemon=True)
+        self.thread.start()
+
+    def run(self):
+        while True:
+            try:
+                c, _ = self.srv.accept()
+            except OSError:
+                return
+            threading.Thread(target=self.serve, args=(c,), daemon=True).start()
+
+    def serve(self, c):
+        with c:
+            while True:
+                hdr = recv_full(c, REQ.size)
+                if hdr is None:
+                    return
+                magic, op, w, h, ch, mode, n = REQ.unpack(hdr)
+                assert magic == MAGIC
+                data = recv_full(c, n)
+                self.requests.append((op, w, h, ch, mode, n))
+                if op == self.fail_op:
+                    c.sendall(REP.pack(MAGIC, -3, 0, b"injected failure"))
+                    continue
+                if op == 1:
+                    img = np.frombuffer(data, np.uint8).reshape(h, w, ch).copy()
+                    out = self.O.gray_inplace(img, ch, fma=bool(mode))
+                else:
+                    out = self.O.sobel(np.frombuffer(data, np.uint8).reshape(h, w).copy(), np.zeros((h, w), np.uint8))
+                c.sendall(REP.pack(MAGIC, 0, n, b"") + out.tobytes())
+
+    def close(self):
+        self.srv.close()
+
+
+def run_client(sock, ch=3, passes=1, extra_env=None):
+    env = dict(os.environ, OMPIMG_WORKER=str(sock), CUDA_VISIBLE_DEVICES="", **(extra_env or {}))
+    return subprocess.run([sys.executable, "-c", CLIENT, str(LIB), str(ch), str(passes)], capture_output=True, text=True, env=env)
+
+
+@pytest.mark.parametrize("ch,passes,mode", [(3, 1, "strict"), (4, 2, "strict"), (3, 1, "fma")])
+def test_frozen_prototypes_go_through_the_worker_without_cuda(O, tmp_path, ch, passes, mode):
+    """CUDA_VISIBLE_DEVICES is empty in the client: any attempt to initialise CUDA there would abort it."""
+    fw = FakeWorker(O, tmp_path / "w.sock")
+    try:
+        r = run_client(tmp_path / "w.sock", ch, passes, {"OMPIMG_LUMA": mode})
+        assert r.returncode == 0, r.stderr
+        got_img, got_edge, launches = r.stdout.split()
+        rng = np.random.default_rng(5)
+        img = rng.integers(0, 256, (37, 53, ch), dtype=np.uint8)
+        for _ in range(passes):
+            img = O.gray_inplace(img, ch, fma=(mode == "fma"))
+        want_edge = O.sobel(np.ascontiguousarray(img[:, :, 0]), np.full((37, 53), 0xAB, np.uint8))    # border bytes stay 0xAB (sobel.c:11-12)
+        assert got_img == sha(img) and got_edge == sha(want_edge)
+        assert launches == "0"                                     # nothing ran in the client process
+        assert [q[0] for q in fw.requests] == [1] * passes + [2]
+        assert all(q[4] == (1 if mode == "fma" else 0) for q in fw.requests if q[0] == 1)
+    finally:
+        fw.close()
+
+
+def test_worker_error_aborts_like_any_other_failure(O, tmp_path):
+    """The frozen functions return void: a worker-side failure ends the process with a message (HTTP 500 upstream)."""
+    fw = FakeWorker(O, tmp_path / "w.sock", fail_op=1)
+    try:
+        r = run_client(tmp_path / "w.sock")
+        assert r.returncode != 0
+        assert "convert_to_grayscale failed" in r.stderr and "injected failure" in r.stderr
+    finally:
+        fw.close()
+
+
+def test_unreachable_worker_means_in_process_cuda_not_a_cpu_path(tmp_path):
+    r = run_client(tmp_path / "nobody.sock")
+    assert "unreachable" in r.stderr
+    if r.returncode != 0:                                          # no GPU visible to the client: it must fail loudly
+        assert "no usable CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+
+
+def test_reference_cli_through_a_worker_matches_the_golden_png(O, golden, tmp_path):
+    """The reference's unmodified main.c linked against the library, served by the (fake) worker: test_gray.png."""
+    exe = ROOT / "oracle" / "_ref" / "bin" / "grayscale_b200"
+    img = ROOT / "oracle" / "_ref" / "fixtures" / "test.jpg"
+    if not exe.exists() or not img.exists():
+        pytest.skip("drop-in binaries not built (oracle/Makefile `dropin`, needs /root/reference at build time)")
+    fw = FakeWorker(O, tmp_path / "w.sock")
+    try:
+        out = tmp_path / "o.png"
+        r = subprocess.run([str(exe), str(img), str(out), "1"], capture_output=True, text=True,
+                           env=dict(os.environ, OMPIMG_WORKER=str(tmp_path / "w.sock"), CUDA_VISIBLE_DEVICES=""))
+        assert r.returncode == 0, r.stderr
+        assert "Compute kernel" in r.stdout
+        assert hashlib.md5(out.read_bytes()).hexdigest() == golden["test_jpg"]["golden_png_md5"]
+    finally:
+        fw.close()
+
+
+# ------------------------------------------------------------------------------------------------ real worker
+@pytest.fixture()
+def real_worker(tmp_path):
+    sock = tmp_path / "gpu.sock"
+    p = subprocess.Popen([str(WORKER), "--socket", str(sock)], stderr=subprocess.PIPE, text=True)
+    t0 = time.time()
+    while not sock.exists():
+        assert p.poll() is None, p.stderr.read()
+        assert time.time() - t0 < 120, "worker did not come up"
+        time.sleep(0.05)
+    time.sleep(0.2)
+    yield sock
+    p.terminate()
+    p.wait(timeout=10)
+
+
+@pytest.mark.gpu
+def test_real_worker_serves_the_frozen_prototypes(O, real_worker):
+    r = run_client(real_worker, 3, 2)
+    assert r.returncode == 0, r.stderr
+    got_img, got_edge, launches = r.stdout.split()
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    for _ in range(2):
+        img = O.gray_inplace(img, 3)
+    want_edge = O.sobel(np.ascontiguousarray(img[:, :, 0]), np.full((37, 53), 0xAB, np.uint8))
+    assert got_img == sha(img) and got_edge == sha(want_edge) and launches == "0"
+
+
+@pytest.mark.gpu
+def test_real_worker_behind_the_reference_cli(golden, real_worker, tmp_path):
+    """BASELINE config 1 and 2 through the worker: byte-identical PNGs, and the per-request cost without the ~3 s of
+    CUDA initialisation a fresh process pays (printed)."""
+    fix = ROOT / "oracle" / "_ref" / "fixtures"
+    exe = ROOT / "oracle" / "_ref" / "bin"
+    if not (exe / "grayscale_b200").exists():
+        pytest.skip("drop-in binaries not built")
+    env = dict(os.environ, OMPIMG_WORKER=str(real_worker), CUDA_VISIBLE_DEVICES="")
+
+    def cli(binary, image, passes, e):
+        out = tmp_path / f"{binary}.png"
+        t0 = time.time()
+        r = subprocess.run([str(exe / binary), str(fix / image), str(out), str(passes)], capture_output=True, text=True, env=e)
+        assert r.returncode == 0, r.stderr
+        return hashlib.md5(out.read_bytes()).hexdigest(), time.time() - t0, r.stdout.strip()
+
+    md5, t_w, line = cli("grayscale_b200", "test.jpg", 1, env)
+    assert md5 == golden["test_jpg"]["golden_png_md5"]
+    md5, t_w3, _ = cli("grayscale_b200", "test.jpg", 3, env)
+    assert md5 == golden["test_jpg"]["strict_p3_png_md5"]
+    md5, t_s, _ = cli("sobel_b200", "more_than_one_mega_photo.jpg", 1, env)
+    assert md5 == golden["photo_jpg"]["strict_p1_png_md5"]
+    md5, t_own, line_own = cli("grayscale_b200", "test.jpg", 1, dict(os.environ))      # own CUDA context
+    assert md5 == golden["test_jpg"]["golden_png_md5"]
+    print(f"\ngrayscale test.jpg x1: worker {t_w:.3f} s [{line}] | own context {t_own:.3f} s [{line_own}] | sobel photo via worker {t_s:.3f} s")
