@@ -144,7 +144,7 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32, CH == 1 ? 3 : 2) sobel_r
     const uint32_t mL = keep(lane == 0 ? 0xffffffffu : 0u);
     const uint32_t mR = keep(lane == 31 ? 0xffffffffu : 0u);
     const size_t dpitch = keep64(p.dst_pitch);
-    uint8_t *out = dst + (size_t)rin0 * p.dst_pitch + x0;     // row of the stage being consumed; stores go one row up
+    uint8_t *out = dst + ((ptrdiff_t)rin0 - 1) * (ptrdiff_t)p.dst_pitch + x0;     // stores go one row above the source row being consumed
     float half = BIAS ? 0.5f : 0.0f;
     if (BIAS) asm volatile("" : "+f"(half));
 
@@ -190,10 +190,10 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32, CH == 1 ? 3 : 2) sobel_r
                 P[2 * j + 1] = prmt(w[j], C64, 0x4342);
                 Q[2 * j + 1] = prmt(w[j], C64, 0x4241);
             }
-            Q[0] = (prmt(lw, w[0], 0x0403) & 0x00ff00ffu) | 0x64006400u;      // (lw.b3, w0.b0) + f16 exponents: PRMT + LOP3
+            Q[0] = prmt(prmt(lw, w[0], 0x0043), C64, 0x4140);                // (lw.b3, w0.b0) + f16 exponents: two PRMT
 #pragma unroll
             for (int j = 1; j < 4; ++j) Q[2 * j] = prmt(P[2 * j - 1], P[2 * j], 0x5432);
-            Q[8] = (prmt(w[3], rw, 0x0403) & 0x00ff00ffu) | 0x64006400u;
+            Q[8] = prmt(prmt(w[3], rw, 0x0043), C64, 0x4140);
         } else {
             uint32_t w[4 * CH];
             load_group_words<CH>(stage, w);
@@ -228,9 +228,8 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32, CH == 1 ? 3 : 2) sobel_r
         }
         if (emit && mode) {
             const uint4 o = sobel_mag16(gx, gy, half);
-            uint8_t *q = out - dpitch;
-            if (mode == 1) *reinterpret_cast<uint4 *>(q) = o;
-            else store_edge16(q, o, mode, plast);
+            if (mode == 1) *reinterpret_cast<uint4 *>(out) = o;
+            else store_edge16(out, o, mode, plast);
         }
         out += dpitch;
         if (rho == 2) {
@@ -388,7 +387,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, CH == 1 ? 3 : 2) sobel_warp_ker
     const uint32_t edge_sh = first ? 8u * (4u - BPP) : 0u;
     const uint32_t mL = first ? 0xffffffffu : 0u, mR = lane == 31 ? 0xffffffffu : 0u;
     const size_t dpitch = p.dst_pitch;
-    uint8_t *out = dst + (size_t)rin0 * p.dst_pitch + x0;     // row of the source row being consumed; stores go one row up
+    uint8_t *out = dst + ((ptrdiff_t)rin0 - 1) * (ptrdiff_t)p.dst_pitch + x0;     // stores go one row above the source row being consumed
     float half = BIAS ? 0.5f : 0.0f;
     if (BIAS) asm volatile("" : "+f"(half));
 
@@ -421,10 +420,10 @@ __global__ void __launch_bounds__(WS_WARPS * 32, CH == 1 ? 3 : 2) sobel_warp_ker
                     P[2 * j + 1] = prmt(w[j], C64, 0x4342);
                     Q[2 * j + 1] = prmt(w[j], C64, 0x4241);
                 }
-                Q[0] = (prmt(lw, w[0], 0x0403) & 0x00ff00ffu) | 0x64006400u;
+                Q[0] = prmt(prmt(lw, w[0], 0x0043), C64, 0x4140);                // (lw.b3, w0.b0) + f16 exponents: two PRMT
 #pragma unroll
                 for (int j = 1; j < 4; ++j) Q[2 * j] = prmt(P[2 * j - 1], P[2 * j], 0x5432);
-                Q[8] = (prmt(w[3], rw, 0x0403) & 0x00ff00ffu) | 0x64006400u;
+                Q[8] = prmt(prmt(w[3], rw, 0x0043), C64, 0x4140);
             } else {
                 uint32_t w[4 * CH];
                 load_group_words<CH>(stage, w);
@@ -461,9 +460,8 @@ __global__ void __launch_bounds__(WS_WARPS * 32, CH == 1 ? 3 : 2) sobel_warp_ker
             }
             if (emit && mode) {
                 const uint4 o = sobel_mag16(gx, gy, half);
-                uint8_t *q = out - dpitch;
-                if (mode == 1) *reinterpret_cast<uint4 *>(q) = o;
-                else store_edge16(q, o, mode, plast);
+                if (mode == 1) *reinterpret_cast<uint4 *>(out) = o;
+                else store_edge16(out, o, mode, plast);
             }
             out += dpitch;
         }
