@@ -24,20 +24,39 @@ def main():
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--rows", type=int, default=8192, help="rows of the square-ish cfg4 image (sums)")
+    ap.add_argument("--natural", action="store_true", help="fused/sobel: frames tiled from the reference's photo instead of uniform noise")
     a = ap.parse_args()
     pkg = importlib.import_module("openmp-parallel-computing_b200")
     pkg.init(0)
     L = pkg.lib()
     W, H, n = a.width, a.height, a.frames
     px = W * H
+    def natural(channels):
+        """one frame tiled from oracle/_ref/fixtures/more_than_one_mega_photo.jpg (a natural image: few saturated edges)"""
+        from PIL import Image
+        img = np.asarray(Image.open(ROOT / "oracle" / "_ref" / "fixtures" / "more_than_one_mega_photo.jpg").convert("RGB"))
+        reps = (-(-H // img.shape[0]), -(-W // img.shape[1]), 1)
+        frame = np.ascontiguousarray(np.tile(img, reps)[:H, :W])
+        if channels == 1:
+            frame = np.ascontiguousarray((frame.astype(np.float32) @ np.array([0.299, 0.587, 0.114], np.float32)).astype(np.uint8))
+        return frame
+
     if a.kernel == "fused":
         src, dst = pkg.DeviceBuffer(n * px * 3), pkg.DeviceBuffer(n * px)
         pkg.synth_dev(src, src.nbytes, 3); dst.fill(0)
+        if a.natural:
+            f = natural(3)
+            for i in range(n):
+                src.upload(f, offset=i * px * 3)
         fn = lambda: L.ompimg_rgb_to_edge_dev(src.ptr, W * 3, 3, dst.ptr, W, W, H, n, px * 3, px, 0)
         bpp = 4
     elif a.kernel == "sobel":
         src, dst = pkg.DeviceBuffer(n * px), pkg.DeviceBuffer(n * px)
         pkg.synth_dev(src, src.nbytes, 2); dst.fill(0)
+        if a.natural:
+            f = natural(1)
+            for i in range(n):
+                src.upload(f, offset=i * px)
         fn = lambda: L.ompimg_sobel_dev(src.ptr, W, dst.ptr, W, W, H, n, px, px, 0)
         bpp = 2
     elif a.kernel == "gray":
