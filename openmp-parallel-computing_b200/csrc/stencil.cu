@@ -259,6 +259,7 @@ struct WarpStencilParams {
     size_t src_pitch, dst_pitch, src_stride, dst_stride;
     int width, height;
     int nbands, rows_per_band, nstrips;
+    const uint8_t *halo_above, *halo_below;   // row-band mode: the source rows -1 / height, in a peer GPU's memory (or nullptr)
     int fold;               // the last strip is at most 256 pixels wide: one warp takes it for TWO bands (16 lanes each)
     int tasks_per_frame;
     long long ntasks;       // nframes * tasks_per_frame, one task per warp
@@ -268,7 +269,7 @@ constexpr int WS_WARPS = 8;
 template <int CH> constexpr int ws_stages() { return CH == 1 ? 4 : 2; }
 template <int CH> constexpr int ws_half_slot() { return 32 + 256 * CH; }          // half a strip and its two 16-byte halo blocks
 template <int CH> constexpr int ws_row_slot() { return 2 * ws_half_slot<CH>(); }
-template <int CH> constexpr int ws_smem() { return WS_WARPS * (ws_stages<CH>() * 3 * ws_row_slot<CH>() + 8 * ws_stages<CH>() + 48) + 128; }
+template <int CH> constexpr int ws_smem() { return WS_WARPS * (ws_stages<CH>() * 3 * ws_row_slot<CH>() + 8 * ws_stages<CH>() + 64) + 128; }
 
 __device__ __forceinline__ bool elect_one_sync() {
     uint32_t pred;
@@ -279,8 +280,8 @@ __device__ __forceinline__ bool elect_one_sync() {
 // rows a band consumes / produces (band 0 takes one output row more, see sobel_rows_kernel)
 __device__ __forceinline__ void ws_band_rows(const WarpStencilParams &p, int band, int &rin0, int &rin1) {
     const int ya = band == 0 ? 0 : band * p.rows_per_band + 1, yb = min(p.height, (band + 1) * p.rows_per_band + 1);
-    rin0 = max(ya - 1, 0);
-    rin1 = band < p.nbands ? min(yb, p.height - 1) : rin0 - 1;      // a band that does not exist consumes nothing
+    rin0 = max(ya - 1, p.halo_above ? -1 : 0);
+    rin1 = band < p.nbands ? min(yb, p.halo_below ? p.height : p.height - 1) : rin0 - 1;      // a band that does not exist consumes nothing
 }
 
 template <int CH, int FMA_MODE, bool BIAS>
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, CH == 1 ? 3 : 2) sobel_warp_ker
     const int lc = folded ? lane & 15 : lane;           // 16-pixel group of the lane inside its (half) strip
     const uint32_t ring0 = (smem_u32(smem) + 127u & ~127u) + (uint32_t)warp * (S * STAGE);
     const uint32_t bar0 = (smem_u32(smem) + 127u & ~127u) + WS_WARPS * (S * STAGE) + (uint32_t)warp * (8 * S);
-    const uint32_t scr0 = (smem_u32(smem) + 127u & ~127u) + WS_WARPS * (S * STAGE + 8 * S) + (uint32_t)warp * 48u;   // see request()
+    const uint32_t scr0 = (smem_u32(smem) + 127u & ~127u) + WS_WARPS * (S * STAGE + 8 * S) + (uint32_t)warp * 64u;   // see request()
 
     const int xs = strip * 512;
     const uint8_t *src = p.src + (size_t)frame * p.src_stride;
@@ -330,10 +331,12 @@ __global__ void __launch_bounds__(WS_WARPS * 32, CH == 1 ? 3 : 2) sobel_warp_ker
     if (lane == 0) {
         const uint32_t lo = xs == 0 ? 0u : (uint32_t)xs * BPP - 16u;
         const uint32_t hi = min(p.row_bytes16, (uint32_t)(xs + (folded ? 256 : 512)) * BPP + 16u);
-        const u64 ga = (u64)(uintptr_t)(src + (size_t)a0 * p.src_pitch + lo), gb = (u64)(uintptr_t)(src + (size_t)max(b0, 0) * p.src_pitch + lo);
+        const u64 ga = (u64)((long long)(uintptr_t)(src + lo) + (long long)a0 * (long long)p.src_pitch);     // a0 is -1 with a halo row above: never dereferenced
+        const u64 gb = (u64)(uintptr_t)(src + (size_t)max(b0, 0) * p.src_pitch + lo);
         sts128(scr0, make_uint4((uint32_t)ga, (uint32_t)(ga >> 32), (uint32_t)gb, (uint32_t)(gb >> 32)));
         sts128(scr0 + 16, make_uint4((uint32_t)a0, (uint32_t)b0, (uint32_t)a1, (uint32_t)b1));
         sts32(scr0 + 32, hi - lo); sts32(scr0 + 36, (xs == 0 ? 16u : 0u) | (nin_b >= 3 ? 256u : 0u));
+        sts32(scr0 + 40, lo);
     }
     __syncwarp();
     auto request = [&](int s) {       // elected lane: the next three rows of each half into stage s (past a band's last row: that row again)
@@ -344,14 +347,35 @@ __global__ void __launch_bounds__(WS_WARPS * 32, CH == 1 ? 3 : 2) sobel_warp_ker
         const int ra1 = (int)c1.z, rb1 = (int)c1.w;
         const bool lb = (fl & 256u) != 0;
         const uint32_t d0 = ring0 + s * STAGE + (fl & 255u), bar = bar0 + 8 * s;
-        mbar_expect_tx(bar, (lb ? 6u : 3u) * bytes);
-        if (!lb && ra_next + 3 <= ra1) {
+        // rows -1 and height of a row band live in a peer GPU's memory: ordinary loads over NVLink by this lane
+        // (two rows per image band; the bulk path does not cross devices here)
+        const bool peer_a = (p.halo_above && ra_next < 0) || (p.halo_below && ra_next + 2 >= p.height && ra1 >= p.height);
+        if (peer_a && !lb) {
+            const uint32_t lo = lds32(scr0 + 40);
+            // bulk copies first, then the plain stores, then the arrive that carries the byte count: the phase cannot
+            // complete before that arrive, and the arrive releases this lane's stores to the lanes that wait
+            uint32_t nbulk = 0;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int r = min(ra_next + j, ra1);
+                if (r >= 0 && r < p.height) { bulk_g2s(d0 + j * ROW_SLOT, reinterpret_cast<const void *>((uintptr_t)ga), bytes, bar); ++nbulk; }
+                else {
+                    const uint8_t *row = (r < 0 ? p.halo_above : p.halo_below) + lo;
+                    for (uint32_t q = 0; q < bytes; q += 16) sts128(d0 + j * ROW_SLOT + q, *reinterpret_cast<const uint4 *>(row + q));
+                }
+                if (ra_next + j < ra1) ga += p.src_pitch;
+            }
+            mbar_expect_tx(bar, nbulk * bytes);
+            ra_next = min(ra_next + 3, ra1);
+        } else if (!lb && ra_next + 3 <= ra1) {
+            mbar_expect_tx(bar, 3u * bytes);
             // the common case (no second half, not at the band's end): three consecutive rows
 #pragma unroll
             for (int j = 0; j < 3; ++j) bulk_g2s(d0 + j * ROW_SLOT, reinterpret_cast<const void *>((uintptr_t)(ga + j * p.src_pitch)), bytes, bar);
             ga += 3 * p.src_pitch;
             ra_next += 3;
         } else {
+            mbar_expect_tx(bar, (lb ? 6u : 3u) * bytes);
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 bulk_g2s(d0 + j * ROW_SLOT, reinterpret_cast<const void *>((uintptr_t)ga), bytes, bar);
@@ -475,6 +499,7 @@ static cudaError_t launch_sobel_warp_t(const StencilArgs &a, int sm_count, cudaS
     p.src = a.src; p.dst = a.dst; p.src_pitch = a.src_pitch; p.dst_pitch = a.dst_pitch;
     p.src_stride = a.src_stride; p.dst_stride = a.dst_stride;
     p.width = a.width; p.height = a.height;
+    p.halo_above = a.halo_above; p.halo_below = a.halo_below;
     p.nstrips = (a.width + 511) / 512;
     p.row_bytes16 = (uint32_t)(((size_t)a.width * CH + 15) & ~(size_t)15);
     // bands of ~130 rows (1 mod 3: each band then consumes a multiple of three source rows); shorter when the launch is small
@@ -486,7 +511,7 @@ static cudaError_t launch_sobel_warp_t(const StencilArgs &a, int sm_count, cudaS
     p.nbands = max(1, (a.height - 1 + rpb - 1) / rpb);
     // a last strip of at most 256 pixels (3840 = 7.5 strips) would leave half a warp idle: fold two bands into one warp
     { static int env = -1; if (env < 0) { const char *e = getenv("OMPIMG_SOBEL_FOLD"); env = e ? atoi(e) : 1; }
-      p.fold = env && p.nbands >= 2 && a.width - (p.nstrips - 1) * 512 <= 256; }
+      p.fold = env && p.nbands >= 2 && a.width - (p.nstrips - 1) * 512 <= 256 && !a.halo_above && !a.halo_below; }
     p.tasks_per_frame = p.fold ? p.nbands * (p.nstrips - 1) + (p.nbands + 1) / 2 : p.nbands * p.nstrips;
     p.ntasks = (long long)a.nframes * p.tasks_per_frame;
     const long long ctas = (p.ntasks + WS_WARPS - 1) / WS_WARPS;
@@ -563,7 +588,7 @@ static cudaError_t launch_sobel_t(const StencilArgs &a, int sm_count, cudaStream
         // warp-autonomous pipeline whenever no halo rows come from peers (OMPIMG_SOBEL_WARP=0: the row-ring kernel, for A/B runs)
         static int warp_mode = -1;
         if (warp_mode < 0) { const char *e = getenv("OMPIMG_SOBEL_WARP"); warp_mode = e ? atoi(e) : 1; }
-        const bool use_warp = !a.halo_above && !a.halo_below && a.height >= 3 && warp_mode != 0;
+        const bool use_warp = warp_mode != 0 && a.height + (a.halo_above ? 1 : 0) + (a.halo_below ? 1 : 0) >= 3;
         if (use_warp) return launch_sobel_warp_t<CH, FMA_MODE, BIAS>(a, sm_count, st);
     }
     StencilParams p{};
