@@ -242,7 +242,7 @@ __global__ void __launch_bounds__((ST_MAX_NW + 1) * 32, CH == 1 ? 3 : 2) sobel_r
 }
 
 // ---------------------------------------------------------------------------------------------
-// Warp-autonomous variant (no halo rows from peers): every warp is its own pipeline.
+// Warp-autonomous variant (the default): every warp is its own pipeline.
 //
 // A warp owns a 512-pixel column strip of a band of rows and runs a private ring of stages (three
 // rows each) with a private mbarrier per stage; an elected lane issues the strip's bulk copies
@@ -347,25 +347,20 @@ __global__ void __launch_bounds__(WS_WARPS * 32, CH == 1 ? 3 : 2) sobel_warp_ker
         const int ra1 = (int)c1.z, rb1 = (int)c1.w;
         const bool lb = (fl & 256u) != 0;
         const uint32_t d0 = ring0 + s * STAGE + (fl & 255u), bar = bar0 + 8 * s;
-        // rows -1 and height of a row band live in a peer GPU's memory: ordinary loads over NVLink by this lane
-        // (two rows per image band; the bulk path does not cross devices here)
+        // rows -1 and height of a row band live in a peer GPU's memory
         const bool peer_a = (p.halo_above && ra_next < 0) || (p.halo_below && ra_next + 2 >= p.height && ra1 >= p.height);
         if (peer_a && !lb) {
             const uint32_t lo = lds32(scr0 + 40);
-            // bulk copies first, then the plain stores, then the arrive that carries the byte count: the phase cannot
-            // complete before that arrive, and the arrive releases this lane's stores to the lanes that wait
-            uint32_t nbulk = 0;
+            // the peer rows come by the same bulk copies, straight over NVLink from the neighbour's allocation
+            mbar_expect_tx(bar, 3u * bytes);
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 const int r = min(ra_next + j, ra1);
-                if (r >= 0 && r < p.height) { bulk_g2s(d0 + j * ROW_SLOT, reinterpret_cast<const void *>((uintptr_t)ga), bytes, bar); ++nbulk; }
-                else {
-                    const uint8_t *row = (r < 0 ? p.halo_above : p.halo_below) + lo;
-                    for (uint32_t q = 0; q < bytes; q += 16) sts128(d0 + j * ROW_SLOT + q, *reinterpret_cast<const uint4 *>(row + q));
-                }
+                const void *row = (r >= 0 && r < p.height) ? reinterpret_cast<const void *>((uintptr_t)ga)
+                                                           : static_cast<const void *>((r < 0 ? p.halo_above : p.halo_below) + lo);
+                bulk_g2s(d0 + j * ROW_SLOT, row, bytes, bar);
                 if (ra_next + j < ra1) ga += p.src_pitch;
             }
-            mbar_expect_tx(bar, nbulk * bytes);
             ra_next = min(ra_next + 3, ra1);
         } else if (!lb && ra_next + 3 <= ra1) {
             mbar_expect_tx(bar, 3u * bytes);
