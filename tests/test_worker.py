@@ -6,6 +6,7 @@ oracle's results (the oracle is the checker, never the product).  GPU tests: the
 serving the reference's unmodified CLI drivers.
 """
 import hashlib
+import mmap
 import os
 import socket
 import struct
@@ -20,7 +21,8 @@ import pytest
 
 from common import ROOT, sha
 
-REQ = struct.Struct("<IIiiiiQ")          # magic, op, width, height, channels, luma_mode, nbytes
+REQ = struct.Struct("<IIiiiiIIQ")        # magic, op, width, height, channels, luma_mode, flags, reserved, nbytes
+WK_SHM, WK_NEWFD = 1, 2
 REP = struct.Struct("<IiQ232s")          # magic, status, nbytes, msg
 MAGIC = 0x4F4D5042
 LIB = ROOT / "openmp-parallel-computing_b200" / "lib" / "libompimg_b200.so"
@@ -72,24 +74,39 @@ class FakeWorker:
             threading.Thread(target=self.serve, args=(c,), daemon=True).start()
 
     def serve(self, c):
+        shm = None
         with c:
             while True:
-                hdr = recv_full(c, REQ.size)
-                if hdr is None:
+                hdr, fds, _, _ = socket.recv_fds(c, REQ.size, 4)           # the mapping's descriptor rides on a header (SCM_RIGHTS)
+                if not hdr:
                     return
-                magic, op, w, h, ch, mode, n = REQ.unpack(hdr)
+                if len(hdr) < REQ.size:
+                    hdr += recv_full(c, REQ.size - len(hdr))
+                if fds:
+                    shm = mmap.mmap(fds[0], 0)
+                    for f in fds:
+                        os.close(f)
+                magic, op, w, h, ch, mode, flags, _, n = REQ.unpack(hdr)
                 assert magic == MAGIC
-                data = recv_full(c, n)
-                self.requests.append((op, w, h, ch, mode, n))
+                assert bool(flags & WK_NEWFD) == bool(fds)
+                if flags & WK_SHM:
+                    data = bytes(shm[:n])
+                else:
+                    data = recv_full(c, n)
+                self.requests.append((op, w, h, ch, mode, n, flags))
                 if op == self.fail_op:
                     c.sendall(REP.pack(MAGIC, -3, 0, b"injected failure"))
                     continue
                 if op == 1:
                     img = np.frombuffer(data, np.uint8).reshape(h, w, ch).copy()
-                    out = self.O.gray_inplace(img, ch, fma=bool(mode))
+                    out, off = self.O.gray_inplace(img, ch, fma=bool(mode)), 0
                 else:
-                    out = self.O.sobel(np.frombuffer(data, np.uint8).reshape(h, w).copy(), np.zeros((h, w), np.uint8))
-                c.sendall(REP.pack(MAGIC, 0, n, b"") + out.tobytes())
+                    out, off = self.O.sobel(np.frombuffer(data, np.uint8).reshape(h, w).copy(), np.zeros((h, w), np.uint8)), (n + 4095) & ~4095
+                if flags & WK_SHM:
+                    shm[off:off + n] = out.tobytes()
+                    c.sendall(REP.pack(MAGIC, 0, n, b""))
+                else:
+                    c.sendall(REP.pack(MAGIC, 0, n, b"") + out.tobytes())
 
     def close(self):
         self.srv.close()
@@ -116,6 +133,8 @@ def test_frozen_prototypes_go_through_the_worker_without_cuda(O, tmp_path, ch, p
         assert got_img == sha(img) and got_edge == sha(want_edge)
         assert launches == "0"                                     # nothing ran in the client process
         assert [q[0] for q in fw.requests] == [1] * passes + [2]
+        # the payload travels through the shared mapping; its descriptor is passed when the mapping is (re)created
+        assert all(q[6] & WK_SHM for q in fw.requests) and fw.requests[0][6] & WK_NEWFD
         assert all(q[4] == (1 if mode == "fma" else 0) for q in fw.requests if q[0] == 1)
     finally:
         fw.close()
@@ -205,10 +224,10 @@ def test_real_worker_behind_the_reference_cli(golden, real_worker, tmp_path):
 
     md5, t_w, line = cli("grayscale_b200", "test.jpg", 1, env)
     assert md5 == golden["test_jpg"]["golden_png_md5"]
-    md5, t_w3, _ = cli("grayscale_b200", "test.jpg", 3, env)
+    md5, t_w3, line3 = cli("grayscale_b200", "test.jpg", 3, env)
     assert md5 == golden["test_jpg"]["strict_p3_png_md5"]
     md5, t_s, _ = cli("sobel_b200", "more_than_one_mega_photo.jpg", 1, env)
     assert md5 == golden["photo_jpg"]["strict_p1_png_md5"]
     md5, t_own, line_own = cli("grayscale_b200", "test.jpg", 1, dict(os.environ))      # own CUDA context
     assert md5 == golden["test_jpg"]["golden_png_md5"]
-    print(f"\ngrayscale test.jpg x1: worker {t_w:.3f} s [{line}] | own context {t_own:.3f} s [{line_own}] | sobel photo via worker {t_s:.3f} s")
+    print(f"\ngrayscale test.jpg x1: worker {t_w:.3f} s [{line}], x3 [{line3}] | own context {t_own:.3f} s [{line_own}] | sobel photo via worker {t_s:.3f} s")
