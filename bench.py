@@ -368,6 +368,13 @@ def other_kernels(pkg, L, peak):
     b = pkg.DeviceBuffer(n1 * w1 * h1 * 3)
     pkg.synth_dev(b, b.nbytes, 1)
     out["gray_inplace_1920x1080x512"] = entry(n1 * w1 * h1, 6, timeit(lambda: L.ompimg_gray_inplace_dev(b.ptr, w1 * 3, w1, h1, 3, n1, w1 * h1 * 3, 0)))
+    # RGB -> packed luma plane (north star (2): 3 B read + 1 B written per pixel), same frames
+    lum = pkg.DeviceBuffer(n1 * w1 * h1)
+    out["rgb_to_luma_1920x1080x512"] = entry(n1 * w1 * h1, 4, timeit(lambda: L.ompimg_rgb_to_luma_dev(b.ptr, w1 * 3, 3, lum.ptr, w1, w1, h1, n1, w1 * h1 * 3, w1 * h1, 0)))
+    # a8: legacy (r+g+b)/3 grayscale with min/max, one 1920 x (1080*512) image
+    mm = pkg.DeviceBuffer(64); g3 = pkg.DeviceBuffer(n1 * w1 * h1 * 3)
+    out["gray_avg3_minmax_1920x552960"] = entry(n1 * w1 * h1, 6, timeit(lambda: L.ompimg_gray_avg3_dev(b.ptr, w1 * 3, g3.ptr, w1 * 3, h1 * n1, w1, mm.ptr, 0)))
+    lum.free(); mm.free(); g3.free()
     b.free()
     # cfg2 shape: Sobel plane->plane, 2000x3000 (pitch 2048) x 128 planes
     w2, h2, p2 = 2000, 3000, 2048
