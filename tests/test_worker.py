@@ -231,3 +231,20 @@ def test_real_worker_behind_the_reference_cli(golden, real_worker, tmp_path):
     md5, t_own, line_own = cli("grayscale_b200", "test.jpg", 1, dict(os.environ))      # own CUDA context
     assert md5 == golden["test_jpg"]["golden_png_md5"]
     print(f"\ngrayscale test.jpg x1: worker {t_w:.3f} s [{line}], x3 [{line3}] | own context {t_own:.3f} s [{line_own}] | sobel photo via worker {t_s:.3f} s")
+
+
+@pytest.mark.gpu
+def test_real_worker_serves_concurrent_clients(O, real_worker):
+    """Several CLI-like clients at once (the services run one process per request): every one gets its own answer."""
+    procs = [subprocess.Popen([sys.executable, "-c", CLIENT, str(LIB), str(3 + (i & 1)), str(1 + i % 3)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                              text=True, env=dict(os.environ, OMPIMG_WORKER=str(real_worker), CUDA_VISIBLE_DEVICES="")) for i in range(8)]
+    for i, p in enumerate(procs):
+        out, err = p.communicate(timeout=120)
+        assert p.returncode == 0, err
+        ch, passes = 3 + (i & 1), 1 + i % 3
+        rng = np.random.default_rng(5)
+        img = rng.integers(0, 256, (37, 53, ch), dtype=np.uint8)
+        for _ in range(passes):
+            img = O.gray_inplace(img, ch)
+        want_edge = O.sobel(np.ascontiguousarray(img[:, :, 0]), np.full((37, 53), 0xAB, np.uint8))
+        assert out.split()[:2] == [sha(img), sha(want_edge)], i
