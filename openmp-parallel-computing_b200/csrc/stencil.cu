@@ -278,13 +278,16 @@ __device__ __forceinline__ bool elect_one_sync() {
 }
 
 // rows a band consumes / produces (band 0 takes one output row more, see sobel_rows_kernel)
+template <bool HALO>
 __device__ __forceinline__ void ws_band_rows(const WarpStencilParams &p, int band, int &rin0, int &rin1) {
     const int ya = band == 0 ? 0 : band * p.rows_per_band + 1, yb = min(p.height, (band + 1) * p.rows_per_band + 1);
-    rin0 = max(ya - 1, p.halo_above ? -1 : 0);
-    rin1 = band < p.nbands ? min(yb, p.halo_below ? p.height : p.height - 1) : rin0 - 1;      // a band that does not exist consumes nothing
+    rin0 = max(ya - 1, HALO && p.halo_above ? -1 : 0);
+    rin1 = band < p.nbands ? min(yb, HALO && p.halo_below ? p.height : p.height - 1) : rin0 - 1;      // a band that does not exist consumes nothing
 }
 
-template <int CH, int FMA_MODE, bool BIAS>
+// HALO: row-band mode, rows -1 / height come from p.halo_above / p.halo_below (a separate instantiation: the extra
+// tests in the request path cost the ordinary launches 5-8 % when compiled in)
+template <int CH, int FMA_MODE, bool BIAS, bool HALO>
 __global__ void __launch_bounds__(WS_WARPS * 32, CH == 1 ? 3 : 2) sobel_warp_kernel(const __grid_constant__ WarpStencilParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int BPP = CH, S = ws_stages<CH>();
@@ -310,8 +313,8 @@ __global__ void __launch_bounds__(WS_WARPS * 32, CH == 1 ? 3 : 2) sobel_warp_ker
     const uint8_t *src = p.src + (size_t)frame * p.src_stride;
     uint8_t *dst = p.dst + (size_t)frame * p.dst_stride;
     int a0, a1, b0, b1;                                 // source rows of the two halves' bands (half B only in folded tasks)
-    ws_band_rows(p, band_a, a0, a1);
-    ws_band_rows(p, folded ? band_a + 1 : p.nbands, b0, b1);
+    ws_band_rows<HALO>(p, band_a, a0, a1);
+    ws_band_rows<HALO>(p, folded ? band_a + 1 : p.nbands, b0, b1);
     const int nin_a = a1 - a0 + 1, nin_b = b1 - b0 + 1;
     const int nin_max = max(nin_a, nin_b);
     if (nin_max < 3) return;
@@ -348,8 +351,8 @@ __global__ void __launch_bounds__(WS_WARPS * 32, CH == 1 ? 3 : 2) sobel_warp_ker
         const bool lb = (fl & 256u) != 0;
         const uint32_t d0 = ring0 + s * STAGE + (fl & 255u), bar = bar0 + 8 * s;
         // rows -1 and height of a row band live in a peer GPU's memory
-        const bool peer_a = (p.halo_above && ra_next < 0) || (p.halo_below && ra_next + 2 >= p.height && ra1 >= p.height);
-        if (peer_a && !lb) {
+        const bool peer_a = HALO && ((p.halo_above && ra_next < 0) || (p.halo_below && ra_next + 2 >= p.height && ra1 >= p.height));
+        if (HALO && peer_a && !lb) {
             const uint32_t lo = lds32(scr0 + 40);
             // the peer rows come by the same bulk copies, straight over NVLink from the neighbour's allocation
             mbar_expect_tx(bar, 3u * bytes);
@@ -488,8 +491,8 @@ __global__ void __launch_bounds__(WS_WARPS * 32, CH == 1 ? 3 : 2) sobel_warp_ker
     }
 }
 
-template <int CH, int FMA_MODE, bool BIAS>
-static cudaError_t launch_sobel_warp_t(const StencilArgs &a, int sm_count, cudaStream_t st) {
+template <int CH, int FMA_MODE, bool BIAS, bool HALO>
+static cudaError_t launch_sobel_warp_h(const StencilArgs &a, int sm_count, cudaStream_t st) {
     WarpStencilParams p{};
     p.src = a.src; p.dst = a.dst; p.src_pitch = a.src_pitch; p.dst_pitch = a.dst_pitch;
     p.src_stride = a.src_stride; p.dst_stride = a.dst_stride;
@@ -498,10 +501,22 @@ static cudaError_t launch_sobel_warp_t(const StencilArgs &a, int sm_count, cudaS
     p.nstrips = (a.width + 511) / 512;
     p.row_bytes16 = (uint32_t)(((size_t)a.width * CH + 15) & ~(size_t)15);
     // bands of ~130 rows (1 mod 3: each band then consumes a multiple of three source rows); shorter when the launch is small
-    const long long want = (long long)sm_count * 24 * 3;
+    // Pick the band height that wastes least: every band re-reads two rows and primes on two rows (2/rows extra), and
+    // a launch of T tasks on S resident warp slots (24 per SM for planes, 16 for RGB(A)) runs in ceil(T/S) waves of
+    // which the last is only partly full.
     int rpb = 130;
+    {
+        static const int choices[] = {130, 100, 82, 64, 46, 34, 25, 16};      // all 1 (mod 3)
+        const double slots = (double)sm_count * (CH == 1 ? 24 : 16);
+        double best = -1.0;
+        for (int c : choices) {
+            const double tasks = (double)a.nframes * p.nstrips * ((a.height - 1 + c - 1) / c);
+            const double waves = tasks / slots, full = waves <= 1.0 ? 1.0 : (double)(long long)(waves + 0.999999);
+            const double eff = waves / full * (double)c / (double)(c + 2);
+            if (eff > best * 1.005) { best = eff; rpb = c; }        // ties go to the taller band
+        }
+    }
     { static int env = -1; if (env < 0) { const char *e = getenv("OMPIMG_SOBEL_BAND"); env = e ? atoi(e) : 0; } if (env > 0) rpb = env; }
-    while (rpb > 16 && (long long)a.nframes * p.nstrips * ((a.height - 1 + rpb - 1) / rpb) < want) rpb = rpb == 130 ? 64 : rpb == 64 ? 34 : 16;
     p.rows_per_band = rpb;
     p.nbands = max(1, (a.height - 1 + rpb - 1) / rpb);
     // a last strip of at most 256 pixels (3840 = 7.5 strips) would leave half a warp idle: fold two bands into one warp
@@ -517,13 +532,18 @@ static cudaError_t launch_sobel_warp_t(const StencilArgs &a, int sm_count, cudaS
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (!(attr_mask >> dev & 1ULL)) {
-        e = cudaFuncSetAttribute(sobel_warp_kernel<CH, FMA_MODE, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        e = cudaFuncSetAttribute(sobel_warp_kernel<CH, FMA_MODE, BIAS, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         attr_mask |= 1ULL << dev;
     }
     count_launch();
-    sobel_warp_kernel<CH, FMA_MODE, BIAS><<<(unsigned)ctas, WS_WARPS * 32, smem, st>>>(p);
+    sobel_warp_kernel<CH, FMA_MODE, BIAS, HALO><<<(unsigned)ctas, WS_WARPS * 32, smem, st>>>(p);
     return cudaGetLastError();
+}
+template <int CH, int FMA_MODE, bool BIAS>
+static cudaError_t launch_sobel_warp_t(const StencilArgs &a, int sm_count, cudaStream_t st) {
+    return (a.halo_above || a.halo_below) ? launch_sobel_warp_h<CH, FMA_MODE, BIAS, true>(a, sm_count, st)
+                                          : launch_sobel_warp_h<CH, FMA_MODE, BIAS, false>(a, sm_count, st);
 }
 
 // ---------------------------------------------------------------------------------------------
