@@ -245,8 +245,34 @@ def run_reference(args, dist: Dist):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def bind_to_gpu_numa_node(local_rank: int):
+    """Run this rank (and first-touch its pinned host buffers) on the CPU socket its GPU hangs off: with several ranks per
+    box the end-to-end leg is bound by host memory and the inter-socket link, not by PCIe alone.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        bus = bus[4:] if len(bus.split(":")[0]) == 8 else bus           # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        return None
+    return None
+
+
 def run_ours(args, dist: Dist):
     pkg = importlib.import_module("openmp-parallel-computing_b200")
+    numa = bind_to_gpu_numa_node(dist.local) if dist.world > 1 and not os.environ.get("OMPIMG_NO_NUMA") else None
     pkg.init(dist.local)
     L = pkg.lib()
     f0, nf = shard(args.frames, dist.rank, dist.world)
@@ -312,7 +338,8 @@ def run_ours(args, dist: Dist):
     assert np.array_equal(edges_host[0][1:-1, 1:-1], edge0[1:-1, 1:-1])       # same result as the resident path
     e2e = {"value": dist.world * ne * PX * args.e2e_steps / dt / 1e9, "unit": "Gpixel/s", "h2d_bytes_per_step": ne * fb, "d2h_bytes_per_step": ne * eb,
            "frames_per_step_per_gpu": ne, "steps": args.e2e_steps, "api": "ompimg_rgb_to_edge_batch_host (pinned host buffers, 8 streams)",
-           "timing": "host wall clock around the synchronous call, max over ranks"}
+           "timing": "host wall clock around the synchronous call, max over ranks",
+           "numa_node_rank0": numa}
     hin.free(); hout.free()
 
     cpu = None
