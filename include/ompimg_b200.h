@@ -172,6 +172,9 @@ OMPIMG_API int ompimg_gray_avg3_host(const uint8_t *rgb, uint8_t *out, int rows,
 OMPIMG_API int ompimg_synth_fill_dev(uint8_t *dst, unsigned long long nbytes, unsigned int seed,
                           unsigned long long byte_offset, int stream);
 
+/* checksum helper: adds the sum of the bytes of a width x rows region (pitch bytes between rows) onto *sum_dev */
+OMPIMG_API int ompimg_byte_sum_dev(const uint8_t *src, size_t pitch, int width, int rows, unsigned long long *sum_dev, int stream);
+
 /* ---- self tests used by tests/ (device arithmetic against closed forms) --------------------------- */
 /* lut[(r<<16)|(g<<8)|b] = luma(r,g,b) for all 2^24 triples, written to HOST memory */
 OMPIMG_API int ompimg_selftest_luma_lut(uint8_t *lut_host, int mode);
@@ -192,6 +195,16 @@ OMPIMG_API int  ompimg_bands_upload(ompimg_bands *b, const uint8_t *rgb_host);  
 OMPIMG_API int  ompimg_bands_rgb_to_edge(ompimg_bands *b, float *ms_max);           /* gray+Sobel on every band, halo via peer access */
 OMPIMG_API int  ompimg_bands_download_edge(ompimg_bands *b, uint8_t *edge_host);    /* dense width*height plane, border bytes untouched */
 OMPIMG_API int  ompimg_bands_checksum(ompimg_bands *b, unsigned long long *sum);    /* sum of all interior edge bytes */
+
+/* one process per GPU (the launcher's form: torchrun, mpirun): the band above / below is another process's
+ * allocation.  ompimg_ipc_export writes the 64-byte CUDA IPC handle of a buffer from ompimg_dev_alloc; the
+ * neighbour passes it to ompimg_ipc_open and gets a device address valid in ITS process (peer access over
+ * NVLink enabled lazily), to be used as row_above / row_below of ompimg_rgb_to_edge_band_dev or as the source
+ * of ompimg_copy_d2d (a P2P copy).  The handle bytes travel by any side channel; no collective is involved. */
+#define OMPIMG_IPC_HANDLE_BYTES 64
+OMPIMG_API int   ompimg_ipc_export(const void *dev_ptr, unsigned char *handle_out /*[OMPIMG_IPC_HANDLE_BYTES]*/);
+OMPIMG_API void *ompimg_ipc_open(const unsigned char *handle);     /* NULL on failure */
+OMPIMG_API int   ompimg_ipc_close(void *mapped);
 
 /* ---- persistent worker mode (the reference's services exec the CLI once per request,
  * microservices/grayscale/app.py:24-34, event-driven/grayscale_service/app.py:54-65) -----------------

@@ -102,6 +102,7 @@ _SIGS = {
     "ompimg_gray_avg3_dev": (C.c_int, [_vp, _sz, _vp, _sz, C.c_int, C.c_int, _vp, C.c_int]),
     "ompimg_gray_avg3_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
     "ompimg_synth_fill_dev": (C.c_int, [_vp, C.c_ulonglong, C.c_uint, C.c_ulonglong, C.c_int]),
+    "ompimg_byte_sum_dev": (C.c_int, [_vp, _sz, C.c_int, C.c_int, _vp, C.c_int]),
     "ompimg_selftest_luma_lut": (C.c_int, [_vp, C.c_int]),
     "ompimg_selftest_isqrt": (C.c_int, [_vp, C.c_uint, C.c_float]),
     "ompimg_bands_create": (_vp, [C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
@@ -112,6 +113,9 @@ _SIGS = {
     "ompimg_bands_rgb_to_edge": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "ompimg_bands_download_edge": (C.c_int, [_vp, _vp]),
     "ompimg_bands_checksum": (C.c_int, [_vp, C.POINTER(C.c_ulonglong)]),
+    "ompimg_ipc_export": (C.c_int, [_vp, _vp]),
+    "ompimg_ipc_open": (_vp, [_vp]),
+    "ompimg_ipc_close": (C.c_int, [_vp]),
     "ompimg_worker_serve": (C.c_int, [C.c_char_p, C.c_int]),
 }
 

@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 #include "../../include/ompimg_b200.h"
 #include "kernels.h"
@@ -41,6 +43,12 @@ __global__ void __launch_bounds__(256) byte_sum_kernel(const uint8_t *src, size_
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+cudaError_t launch_byte_sum(const uint8_t *src, size_t pitch, int width, int rows, unsigned long long *sum_dev, int sm_count, cudaStream_t st) {
+    count_launch();
+    byte_sum_kernel<<<sm_count * 8, 256, 0, st>>>(src, pitch, 0, width, 0, rows, sum_dev);
+    return cudaGetLastError();
 }
 
 }  // namespace ompimg
@@ -173,32 +181,48 @@ extern "C" int ompimg_bands_upload(ompimg_bands *b, const uint8_t *rgb_host) {
     return bands_sync(b);
 }
 
+// enqueue one band's work on its device: start event, (staged halo copies where peer access is missing,) kernel, stop event
+static int bands_enqueue(ompimg_bands *b, int i, int mode, int no_bias) {
+    BCK(cudaSetDevice(b->dev[i]));
+    const int rows = b->row0[i + 1] - b->row0[i];
+    BCK(cudaEventRecord(b->e0[i], b->st[i]));
+    const uint8_t *above = nullptr, *below = nullptr;
+    if (i > 0) {
+        const uint8_t *peer_row = b->rgb[i - 1] + (size_t)(b->row0[i] - b->row0[i - 1] - 1) * b->rpitch;
+        if (b->direct[i][0]) above = peer_row;
+        else { BCK(cudaMemcpyPeerAsync(b->halo[i], b->dev[i], peer_row, b->dev[i - 1], b->rpitch, b->st[i])); above = b->halo[i]; }
+    }
+    if (i + 1 < b->ndev) {
+        const uint8_t *peer_row = b->rgb[i + 1];
+        if (b->direct[i][1]) below = peer_row;
+        else { BCK(cudaMemcpyPeerAsync(b->halo[i] + b->rpitch, b->dev[i], peer_row, b->dev[i + 1], b->rpitch, b->st[i])); below = b->halo[i] + b->rpitch; }
+    }
+    StencilArgs a{};
+    a.src = b->rgb[i]; a.dst = b->edge[i]; a.src_pitch = b->rpitch; a.dst_pitch = b->epitch;
+    a.width = b->w; a.height = rows; a.channels = b->ch; a.nframes = 1; a.fma_mode = mode;
+    a.halo_above = above; a.halo_below = below;
+    a.no_bias = no_bias;
+    BCK(launch_sobel(a, b->sm_count[i], b->st[i]));
+    BCK(cudaEventRecord(b->e1[i], b->st[i]));
+    return OMPIMG_OK;
+}
+
+// The bands' kernels are short (0.1 ms on 8 GPUs for 32768^2), so the launches must not queue up behind one host
+// thread: every device gets its own launching thread (env OMPIMG_BANDS_THREADS=0: one thread, for A/B runs).
 extern "C" int ompimg_bands_rgb_to_edge(ompimg_bands *b, float *ms_max) {
     if (!b) return OMPIMG_ERR_ARG;
-    const int mode = ompimg_get_luma_mode();
-    for (int i = 0; i < b->ndev; ++i) {
-        BCK(cudaSetDevice(b->dev[i]));
-        const int rows = b->row0[i + 1] - b->row0[i];
-        BCK(cudaEventRecord(b->e0[i], b->st[i]));
-        const uint8_t *above = nullptr, *below = nullptr;
-        if (i > 0) {
-            const uint8_t *peer_row = b->rgb[i - 1] + (size_t)(b->row0[i] - b->row0[i - 1] - 1) * b->rpitch;
-            if (b->direct[i][0]) above = peer_row;
-            else { BCK(cudaMemcpyPeerAsync(b->halo[i], b->dev[i], peer_row, b->dev[i - 1], b->rpitch, b->st[i])); above = b->halo[i]; }
-        }
-        if (i + 1 < b->ndev) {
-            const uint8_t *peer_row = b->rgb[i + 1];
-            if (b->direct[i][1]) below = peer_row;
-            else { BCK(cudaMemcpyPeerAsync(b->halo[i] + b->rpitch, b->dev[i], peer_row, b->dev[i + 1], b->rpitch, b->st[i])); below = b->halo[i] + b->rpitch; }
-        }
-        StencilArgs a{};
-        a.src = b->rgb[i]; a.dst = b->edge[i]; a.src_pitch = b->rpitch; a.dst_pitch = b->epitch;
-        a.width = b->w; a.height = rows; a.channels = b->ch; a.nframes = 1; a.fma_mode = mode;
-        a.halo_above = above; a.halo_below = below;
-        a.no_bias = sqrt_exact_flag();
-        BCK(launch_sobel(a, b->sm_count[i], b->st[i]));
-        BCK(cudaEventRecord(b->e1[i], b->st[i]));
+    const int mode = ompimg_get_luma_mode(), no_bias = sqrt_exact_flag();
+    static int threaded = -1;
+    if (threaded < 0) { const char *e = getenv("OMPIMG_BANDS_THREADS"); threaded = e ? atoi(e) : 1; }
+    int rcs[16] = {};
+    if (threaded && b->ndev > 1) {
+        std::vector<std::thread> th;
+        for (int i = 0; i < b->ndev; ++i) th.emplace_back([&, i] { rcs[i] = bands_enqueue(b, i, mode, no_bias); });
+        for (auto &t : th) t.join();
+    } else {
+        for (int i = 0; i < b->ndev; ++i) rcs[i] = bands_enqueue(b, i, mode, no_bias);
     }
+    for (int i = 0; i < b->ndev; ++i) if (rcs[i]) return rcs[i];
     float mx = 0.f;
     for (int i = 0; i < b->ndev; ++i) {
         BCK(cudaSetDevice(b->dev[i]));
@@ -250,5 +274,36 @@ extern "C" int ompimg_bands_checksum(ompimg_bands *b, unsigned long long *sum) {
     }
     BCK(cudaSetDevice(b->home));
     *sum = total;
+    return OMPIMG_OK;
+}
+
+// ---- one process per GPU: the neighbour's band is another PROCESS's allocation --------------------------------
+// CUDA IPC maps it into this process (cudaIpcOpenMemHandle enables peer access lazily), after which the address is
+// used exactly like a same-process peer pointer: the stencil kernel's bulk copies fetch the halo row over NVLink.
+// The 64-byte handle travels by whatever side channel the launcher has (bench.py: torch.distributed all_gather).
+static_assert(sizeof(cudaIpcMemHandle_t) == OMPIMG_IPC_HANDLE_BYTES, "IPC handle size");
+extern "C" int ompimg_ipc_export(const void *dev_ptr, unsigned char *handle_out) {
+    if (!dev_ptr || !handle_out) return OMPIMG_ERR_ARG;
+    cudaIpcMemHandle_t h;
+    BCK(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+    memcpy(handle_out, &h, sizeof h);
+    return OMPIMG_OK;
+}
+extern "C" void *ompimg_ipc_open(const unsigned char *handle) {
+    if (!handle) return nullptr;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "libompimg_b200: cudaIpcOpenMemHandle failed: %s\n", cudaGetErrorString(e));
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" int ompimg_ipc_close(void *mapped) {
+    if (!mapped) return OMPIMG_OK;
+    BCK(cudaIpcCloseMemHandle(mapped));
     return OMPIMG_OK;
 }

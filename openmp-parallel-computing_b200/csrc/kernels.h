@@ -59,6 +59,9 @@ cudaError_t launch_sobel(const StencilArgs &a, int sm_count, cudaStream_t st);
 int sqrt_exact_flag();          // runtime.cu: 1 when the bound device passed the exhaustive MUFU.SQRT check
 cudaError_t launch_isqrt_selftest(uint8_t *out_dev, unsigned int count, float bias, cudaStream_t st);
 
+// bands.cu: sum of the bytes of a width x rows region, added onto *sum_dev
+cudaError_t launch_byte_sum(const uint8_t *src, size_t pitch, int width, int rows, unsigned long long *sum_dev, int sm_count, cudaStream_t st);
+
 // conv.cu -----------------------------------------------------------------------------------------
 cudaError_t launch_conv(const uint8_t *in, size_t in_pitch, int rows, int cols, int K, const int32_t *taps_host, int32_t norm,
                         void *out, size_t out_pitch, int out_is_u8, int sm_count, cudaStream_t st);

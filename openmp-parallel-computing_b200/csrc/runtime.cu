@@ -535,6 +535,13 @@ extern "C" int ompimg_gray_avg3_dev(const uint8_t *rgb, size_t ip, uint8_t *out,
     CK(launch_gray_avg3(rgb, ip, out, op, rows, cols, min_max, g.sm_count, st));
     return OMPIMG_OK;
 }
+extern "C" int ompimg_byte_sum_dev(const uint8_t *src, size_t pitch, int width, int rows, unsigned long long *sum_dev, int stream) {
+    INIT(); STREAM(stream, st);
+    NEED(src && sum_dev && width >= 0 && rows >= 0 && pitch >= (size_t)width, "region");
+    if (width == 0 || rows == 0) return OMPIMG_OK;
+    CK(launch_byte_sum(src, pitch, width, rows, sum_dev, g.sm_count, st));
+    return OMPIMG_OK;
+}
 extern "C" int ompimg_synth_fill_dev(uint8_t *dst, unsigned long long nbytes, unsigned int seed, unsigned long long off, int stream) {
     INIT(); STREAM(stream, st);
     NEED(dst || nbytes == 0, "dst");

@@ -506,10 +506,9 @@ static cudaError_t launch_sobel_warp_h(const StencilArgs &a, int sm_count, cudaS
     // which the last is only partly full.
     int rpb = 130;
     {
-        static const int choices[] = {130, 100, 82, 64, 46, 34, 25, 16};      // all 1 (mod 3)
         const double slots = (double)sm_count * (CH == 1 ? 24 : 16);
         double best = -1.0;
-        for (int c : choices) {
+        for (int c = 130; c >= 16; c -= 3) {                                    // all 1 (mod 3)
             const double tasks = (double)a.nframes * p.nstrips * ((a.height - 1 + c - 1) / c);
             const double waves = tasks / slots, full = waves <= 1.0 ? 1.0 : (double)(long long)(waves + 0.999999);
             const double eff = waves / full * (double)c / (double)(c + 2);

@@ -9,7 +9,7 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this; the product never does.
  *
- * Pinning: `make -C oracle check` (and tests/test_oracle_vs_ref.py) compare every
+ * Pinning: `make -C oracle check` (= tests/test_oracle.py) compare every
  * function here against the UNMODIFIED reference sources compiled into
  * oracle/_ref/ (see Makefile), and the grayscale path against the reference's one
  * golden vector images/test_gray.png.
@@ -30,6 +30,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <string.h>
+#include <stdlib.h>
 
 #define ORACLE_API __attribute__((visibility("default")))
 
@@ -313,3 +314,24 @@ ORACLE_API void oracle_synth_fill(unsigned char *dst, unsigned long long nbytes,
         dst[i] = (unsigned char)(w >> (8 * (gi & 3)));
     }
 }
+
+/* --- harness helpers (no pixel math) ------------------------------------------
+ * The OpenMP thread count the runtime will really use (bench.py prints this, not os.cpu_count()). */
+#include <omp.h>
+ORACLE_API int oracle_omp_max_threads(void) { return omp_get_max_threads(); }
+
+/* The reference's old/ output parameters are `long ***` tables (old/parallel_convolution.c:8,
+ * old/parallel_to_grayscale.c:7); building one with a million ctypes casts is too slow for the timed
+ * CPU baseline, so it is built here over a dense rows x cols x 3 `long` array. */
+ORACLE_API void *oracle_table3_alloc(long *base, int rows, int cols)
+{
+    long ***top = (long ***)malloc((size_t)rows * sizeof(long **) + (size_t)rows * cols * sizeof(long *));
+    if (!top) return NULL;
+    long **cells = (long **)(top + rows);
+    for (int r = 0; r < rows; ++r) {
+        top[r] = cells + (size_t)r * cols;
+        for (int c = 0; c < cols; ++c) top[r][c] = base + ((size_t)r * cols + c) * 3;
+    }
+    return top;
+}
+ORACLE_API void oracle_table3_free(void *t) { free(t); }

@@ -60,6 +60,11 @@ def lib() -> C.CDLL:
         L.oracle_extract_plane.argtypes = [_u8p, C.c_longlong, C.c_int, _u8p]
         L.oracle_replicate_plane.argtypes = [_u8p, C.c_longlong, C.c_int, _u8p]
         L.oracle_synth_fill.argtypes = [_u8p, C.c_ulonglong, C.c_uint, C.c_ulonglong]
+        L.oracle_omp_max_threads.restype = C.c_int
+        L.oracle_table3_alloc.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.oracle_table3_alloc.restype = C.c_void_p
+        L.oracle_table3_free.argtypes = [C.c_void_p]
+        L.oracle_table3_free.restype = None
         for f in ("oracle_gray_inplace oracle_gray_lut oracle_rgb_to_luma oracle_sobel oracle_sobel_isqrt "
                   "oracle_gray_sobel_pass oracle_rgb_to_edge oracle_convolution_long oracle_convolution_u8 "
                   "oracle_avg_pixel_long oracle_avg_pixel_u8 oracle_gray_avg3_long oracle_gray_avg3_u8 "
@@ -278,18 +283,17 @@ class RefOld:
 
     @staticmethod
     def _table3(arr: np.ndarray):
-        """Build the long*** pointer table the reference's output parameters expect."""
+        """The long*** pointer table the reference's output parameters expect (built in C: oracle_table3_alloc)."""
         rows, cols, _ = arr.shape
-        LP = C.POINTER(C.c_long)
-        row_tabs, keep = [], []
-        for r in range(rows):
-            t = (LP * cols)()
-            for c in range(cols):
-                t[c] = C.cast(arr[r, c].ctypes.data, LP)
-            keep.append(t)
-            row_tabs.append(C.cast(t, C.POINTER(LP)))
-        top = (C.POINTER(LP) * rows)(*row_tabs)
-        return top, keep
+        assert arr.dtype == np.int64 and arr.flags.c_contiguous
+        t = lib().oracle_table3_alloc(arr.ctypes.data, rows, cols)
+        if not t:
+            raise MemoryError("oracle_table3_alloc")
+
+        class _Keep:
+            def __del__(self_inner, t=t):
+                lib().oracle_table3_free(t)
+        return C.c_void_p(t), _Keep()
 
     def convolution(self, padded: np.ndarray, kernel: np.ndarray, out: np.ndarray) -> np.ndarray:
         assert padded.shape == (self.rows + self.K - 1, self.cols + self.K - 1, 3) and padded.dtype == np.int64
@@ -308,6 +312,14 @@ class RefOld:
         top, keep = self._table3(out)
         self.L.parallel_to_grayscale(C.c_void_p(img.ctypes.data), top, C.c_void_p(mm.ctypes.data))
         return out, mm
+
+
+def omp_max_threads() -> int:
+    return int(lib().oracle_omp_max_threads())
+
+
+def have_ref_old(rows: int, cols: int, K: int, norm: int) -> bool:
+    return (REF_DIR / f"libref_old_{rows}_{cols}_{K}_{norm}.so").exists()
 
 
 def have_ref(variant: str = "strict") -> bool:

@@ -332,6 +332,25 @@ def test_row_bands_equal_single_pass(gpu, O):
     b.close()
 
 
+def test_row_bands_on_distinct_devices_equal_oracle(gpu, O):
+    """the real peer path: every band on its own GPU, halo rows fetched by the kernel's bulk copies over NVLink
+    (skips on a one-GPU box; `gpurun --gpus 2` and the 8-GPU scaling run exercise it)"""
+    ndev = gpu.lib().ompimg_device_count()
+    if ndev < 2:
+        pytest.skip("needs at least two GPUs")
+    for w, h in ((1500, 257), (8192, 1040)):
+        rgb = O.synth(h * w * 3, 0xB2000005).reshape(h, w, 3)
+        want = O.rgb_to_edge(rgb)
+        for n in sorted({2, min(ndev, 4), min(ndev, 8)}):
+            b = gpu.Bands(w, h, 3, list(range(n)))
+            b.upload(rgb)
+            b.rgb_to_edge()
+            b.rgb_to_edge()
+            assert np.array_equal(b.download_edge(), want), (w, h, n)
+            assert b.checksum() == int(want[1:-1, 1:-1].astype(np.int64).sum())
+            b.close()
+
+
 @pytest.mark.parametrize("w", [17, 511, 512, 513, 2047, 4096, 4097, 4112, 8191])
 @pytest.mark.parametrize("h", [3, 4, 5, 6, 7, 17, 130, 131, 132, 133, 134, 262, 263, 264])
 def test_sobel_and_fused_tricky_shapes(gpu, O, w, h):
