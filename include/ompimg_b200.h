@@ -144,14 +144,22 @@ OMPIMG_API int ompimg_rgb_to_edge_batch_host(const uint8_t *rgb, size_t rgb_stri
  * out[r][c][p] = (sum_{kr,kc} in[r+kr][c+kc][p] * taps[kr*K+kc]) / norm  (C truncating division,
  * no clamp).  Input is pre-padded: (rows+K-1) x (cols+K-1) interleaved uint8 RGB, top-left
  * anchored exactly like the reference.  Output int32 RGB (rows x cols x 3, dense) or, with
- * ompimg_conv_u8_dev, uint8 (values outside 0..255 are an error the caller excludes by choice of
- * taps: box/Gaussian kernels with norm = sum(taps) stay in range).  K odd or even, 1..15. */
+ * ompimg_conv_u8_dev, uint8.  The reference does not clamp (old/parallel_convolution.c:20), and neither does the
+ * uint8 form: it stores (uint8_t)value, i.e. the low 8 bits of the exact int32 result -- what a C caller gets by
+ * narrowing the reference's `long`.  Box/Gaussian taps with norm = sum(taps) never leave 0..255; for taps that can
+ * (negative taps, sum(taps) > norm) use ompimg_conv_i32_dev unless that wrap is what you want.  K odd or even, 1..15.
+ * in_pitch >= (cols+K-1)*3 and out_pitch >= cols*3 elements of the output type, else OMPIMG_ERR_ARG. */
 OMPIMG_API int ompimg_conv_i32_dev(const uint8_t *in, size_t in_pitch, int rows, int cols, int K,
                         const int32_t *taps_host, int32_t norm, int32_t *out, size_t out_pitch, int stream);
 OMPIMG_API int ompimg_conv_u8_dev(const uint8_t *in, size_t in_pitch, int rows, int cols, int K,
                        const int32_t *taps_host, int32_t norm, uint8_t *out, size_t out_pitch, int stream);
 OMPIMG_API int ompimg_conv_i32_host(const uint8_t *in_padded, int rows, int cols, int K,
                          const int32_t *taps, int32_t norm, int32_t *out);
+/* the reference's exact statement: it ACCUMULATES the tap sums onto the caller's array and then divides
+ * (old/parallel_convolution.c:17,20), so out = (out_on_entry + sum) / norm.  ompimg_conv_i32_host is the case every
+ * caller of the reference sets up (a zeroed array). */
+OMPIMG_API int ompimg_conv_i32_accum_host(const uint8_t *in_padded, int rows, int cols, int K,
+                               const int32_t *taps, int32_t norm, int32_t *out_inout);
 
 /* ---- a7: average pixel (old/parallel_avg_pixel.c:5-42) -------------------------------------------
  * sums[c] = sum of channel c over rows x cols RGB pixels (exact, 64-bit).  The reference's

@@ -97,6 +97,7 @@ _SIGS = {
     "ompimg_conv_i32_dev": (C.c_int, [_vp, _sz, C.c_int, C.c_int, C.c_int, _vp, C.c_int32, _vp, _sz, C.c_int]),
     "ompimg_conv_u8_dev": (C.c_int, [_vp, _sz, C.c_int, C.c_int, C.c_int, _vp, C.c_int32, _vp, _sz, C.c_int]),
     "ompimg_conv_i32_host": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int32, _vp]),
+    "ompimg_conv_i32_accum_host": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int32, _vp]),
     "ompimg_channel_sums_dev": (C.c_int, [_vp, _sz, C.c_int, C.c_int, _vp, C.c_int]),
     "ompimg_avg_pixel_host": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "ompimg_gray_avg3_dev": (C.c_int, [_vp, _sz, _vp, _sz, C.c_int, C.c_int, _vp, C.c_int]),
@@ -130,6 +131,8 @@ def lib() -> C.CDLL:
             raise OmpimgError(f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
         L = C.CDLL(str(LIB_PATH))
         for name, (res, args) in _SIGS.items():
+            if "OMPIMG_LIB" in os.environ and not hasattr(L, name):
+                continue                   # an older A/B build of the library (tools/ only): newer entry points are simply absent
             fn = getattr(L, name)          # AttributeError = a declared symbol is not exported
             fn.restype, fn.argtypes = res, args
         _lib = L
@@ -257,7 +260,11 @@ def convert_to_grayscale(data: np.ndarray, width: int | None = None, height: int
     """monolithic/include/parallel_to_grayscale.h:4 -- in place on an HxWxC (or flat) uint8 array."""
     _u8c(data, "data")
     if width is None:
+        if data.ndim != 3:
+            raise ValueError("data must be H x W x C when width/height/channels are not given")
         height, width, channels = data.shape
+    elif data.size < width * height * channels:
+        raise ValueError("data holds fewer than width*height*channels bytes")
     _ck(lib().ompimg_gray_inplace_host(_ptr(data), width, height, channels), "convert_to_grayscale")
     return data
 
@@ -265,6 +272,8 @@ def convert_to_grayscale(data: np.ndarray, width: int | None = None, height: int
 def sobel_edge(src: np.ndarray, dst: np.ndarray | None = None) -> np.ndarray:
     """monolithic/include/sobel.h:3-5 -- dst border bytes are left exactly as they were."""
     _u8c(src, "src")
+    if src.ndim != 2:
+        raise ValueError("src must be an H x W plane")
     h, w = src.shape
     if dst is None:
         dst = np.zeros((h, w), np.uint8)
@@ -278,6 +287,8 @@ def sobel_edge(src: np.ndarray, dst: np.ndarray | None = None) -> np.ndarray:
 def gray_sobel_pass(img: np.ndarray, edge: np.ndarray | None = None):
     """One iteration of monolithic/src/main_with_sobel.c:51-74, in place on img (HxWxC)."""
     _u8c(img, "img")
+    if img.ndim != 3 or img.shape[2] not in (3, 4):
+        raise ValueError("img must be H x W x 3 or H x W x 4")
     h, w, ch = img.shape
     if edge is not None:
         _u8c(edge, "edge")
@@ -290,6 +301,8 @@ def gray_sobel_pass(img: np.ndarray, edge: np.ndarray | None = None):
 def rgb_to_edge_batch(frames: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
     """Fused gray->Sobel on a batch NxHxWxC; returns NxHxW edge planes with zero borders."""
     _u8c(frames, "frames")
+    if frames.ndim != 4 or frames.shape[3] not in (3, 4):
+        raise ValueError("frames must be N x H x W x 3 or N x H x W x 4")
     n, h, w, ch = frames.shape
     if out is None:
         out = np.empty((n, h, w), np.uint8)
@@ -297,20 +310,38 @@ def rgb_to_edge_batch(frames: np.ndarray, out: np.ndarray | None = None) -> np.n
     return out
 
 
-def parallel_convolution(padded: np.ndarray, kernel: np.ndarray, norm: int) -> np.ndarray:
-    """old/parallel_convolution.c:8-24 on uint8 storage with a zeroed output; returns int32 rows x cols x 3."""
-    _u8c(padded, "padded")
+def _rgb3(a: np.ndarray, name: str) -> np.ndarray:
+    _u8c(a, name)
+    if a.ndim != 3 or a.shape[2] != 3:
+        raise ValueError(f"{name} must be rows x cols x 3 (got shape {a.shape})")
+    return a
+
+
+def parallel_convolution(padded: np.ndarray, kernel: np.ndarray, norm: int, out: np.ndarray | None = None) -> np.ndarray:
+    """old/parallel_convolution.c:8-24 on uint8 storage; returns int32 rows x cols x 3.  With `out` (int32, rows x cols x 3)
+    the reference's own accumulate-then-divide statement applies: out = (out + sum) / norm (:17,:20)."""
+    _rgb3(padded, "padded")
+    kernel = np.asarray(kernel)
+    if kernel.ndim != 2 or kernel.shape[0] != kernel.shape[1]:
+        raise ValueError("kernel must be K x K")
     K = int(kernel.shape[0])
     rows, cols = padded.shape[0] - K + 1, padded.shape[1] - K + 1
+    if rows <= 0 or cols <= 0:
+        raise ValueError("padded must be (rows+K-1) x (cols+K-1) x 3")
     taps = np.ascontiguousarray(kernel, np.int32)
-    out = np.empty((rows, cols, 3), np.int32)
-    _ck(lib().ompimg_conv_i32_host(_ptr(padded), rows, cols, K, _ptr(taps), int(norm), _ptr(out)), "parallel_convolution")
+    if out is None:
+        out = np.empty((rows, cols, 3), np.int32)
+        _ck(lib().ompimg_conv_i32_host(_ptr(padded), rows, cols, K, _ptr(taps), int(norm), _ptr(out)), "parallel_convolution")
+        return out
+    if not (isinstance(out, np.ndarray) and out.dtype == np.int32 and out.flags.c_contiguous and out.shape == (rows, cols, 3)):
+        raise ValueError("out must be a C-contiguous int32 array of shape rows x cols x 3")
+    _ck(lib().ompimg_conv_i32_accum_host(_ptr(padded), rows, cols, K, _ptr(taps), int(norm), _ptr(out)), "parallel_convolution (accumulate)")
     return out
 
 
 def parallel_avg_pixel(img: np.ndarray, avgs=(0, 0, 0)) -> np.ndarray:
     """old/parallel_avg_pixel.c:5-42 (accumulates onto avgs, then divides by rows*cols*3)."""
-    _u8c(img, "img")
+    _rgb3(img, "img")
     a = np.array(avgs, np.int64)
     _ck(lib().ompimg_avg_pixel_host(_ptr(img), img.shape[0], img.shape[1], _ptr(a)), "parallel_avg_pixel")
     return a
@@ -318,7 +349,7 @@ def parallel_avg_pixel(img: np.ndarray, avgs=(0, 0, 0)) -> np.ndarray:
 
 def parallel_to_grayscale(img: np.ndarray):
     """old/parallel_to_grayscale.c:7-38: (r+g+b)/3 to all channels and {min, max}."""
-    _u8c(img, "img")
+    _rgb3(img, "img")
     out = np.empty_like(img)
     mm = np.zeros(2, np.int32)
     _ck(lib().ompimg_gray_avg3_host(_ptr(img), _ptr(out), img.shape[0], img.shape[1], _ptr(mm)), "parallel_to_grayscale")

@@ -15,6 +15,8 @@
 //   * generic: the same column walk with K*K MACs per input row into K rotating accumulators.
 // Taps travel as kernel parameters (constant bank, uniform access).  Accumulation is int32 when
 // 255*sum|taps| < 2^31, else int64.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -359,6 +361,26 @@ cudaError_t launch_conv(const uint8_t *in, size_t in_pitch, int rows, int cols, 
         if (wide) { count_launch(); conv_direct_kernel<long long><<<grid, 256, 0, st>>>(p, taps, K); }
         else { count_launch(); conv_direct_kernel<int32_t><<<grid, 256, 0, st>>>(p, taps, K); }
     }
+    return cudaGetLastError();
+}
+
+// out = (prior + out) / norm, C division: the accumulate-then-divide of old/parallel_convolution.c:17,20 for callers whose
+// output array is not zero on entry (`out` holds the raw tap sums, computed with norm 1)
+__global__ void __launch_bounds__(256) accum_div_kernel(int32_t *out, size_t out_pitch, const int32_t *prior, size_t prior_pitch, int rows, int n, int32_t norm) {
+    const long long total = (long long)rows * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / n, c = i - r * n;
+        int32_t *o = reinterpret_cast<int32_t *>(reinterpret_cast<uint8_t *>(out) + (size_t)r * out_pitch) + c;
+        const int32_t pr = *(reinterpret_cast<const int32_t *>(reinterpret_cast<const uint8_t *>(prior) + (size_t)r * prior_pitch) + c);
+        *o = (int32_t)(((long long)pr + (long long)*o) / (long long)norm);
+    }
+}
+cudaError_t launch_accum_div(int32_t *out, size_t out_pitch, const int32_t *prior, size_t prior_pitch, int rows, int n, int32_t norm, int sm_count, cudaStream_t st) {
+    if (rows <= 0 || n <= 0) return cudaSuccess;
+    const long long total = (long long)rows * n;
+    const int grid = (int)std::max(1LL, std::min((total + 255) / 256, (long long)sm_count * 16));
+    count_launch();
+    accum_div_kernel<<<grid, 256, 0, st>>>(out, out_pitch, prior, prior_pitch, rows, n, norm);
     return cudaGetLastError();
 }
 

@@ -66,6 +66,9 @@ cudaError_t launch_byte_sum(const uint8_t *src, size_t pitch, int width, int row
 cudaError_t launch_conv(const uint8_t *in, size_t in_pitch, int rows, int cols, int K, const int32_t *taps_host, int32_t norm,
                         void *out, size_t out_pitch, int out_is_u8, int sm_count, cudaStream_t st);
 
+cudaError_t launch_accum_div(int32_t *out, size_t out_pitch, const int32_t *prior, size_t prior_pitch, int rows, int n, int32_t norm,
+                             int sm_count, cudaStream_t st);
+
 // conv_sep.cu: rank-1 taps u (vertical) x v (horizontal); false = outside its ranges, nothing launched
 bool launch_conv_sep(const uint8_t *in, size_t in_pitch, int rows, int cols, int K, const int32_t *u, const int32_t *v, int32_t norm,
                      void *out, size_t out_pitch, int out_is_u8, int sm_count, cudaStream_t st, cudaError_t *err);

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -42,7 +43,7 @@ struct Ctx {
     cudaStream_t streams[OMPIMG_NUM_STREAMS] = {};
     cudaEvent_t edge_events[OMPIMG_NUM_STREAMS] = {};
     std::vector<Timer> timers;
-    DevBuf scratch[4];                       // host-API staging on the device
+    DevBuf scratch[5];                       // host-API staging on the device
     DevBuf slots[OMPIMG_NUM_STREAMS][2];     // per-stream (input, output) slots of the batch pipeline
     DevBuf pin[3];                           // pinned host staging for pageable caller buffers (grow-only)
     std::vector<cudaEvent_t> chunk_events;   // one per in-flight chunk of a staged download
@@ -494,6 +495,7 @@ extern "C" int ompimg_replicate_dev(const uint8_t *plane, size_t pp, uint8_t *im
     INIT(); STREAM(stream, st);
     NEED(plane && img && w > 0 && h > 0 && nframes > 0, "image");
     NEED(ch == 3 || ch == 4, "channels must be 3 or 4");
+    NEED(pp >= (size_t)w && ip >= (size_t)w * ch, "pitch");
     CK(launch_replicate(plane, pp, img, ip, ch, w, h, nframes, ps, is, g.sm_count, st));
     return OMPIMG_OK;
 }
@@ -512,6 +514,7 @@ extern "C" int ompimg_conv_i32_dev(const uint8_t *in, size_t in_pitch, int rows,
     INIT(); STREAM(stream, st);
     NEED(in && out && taps && rows > 0 && cols > 0, "image");
     NEED(K >= 1 && K <= 15 && norm != 0, "K in 1..15, norm != 0");
+    NEED(in_pitch >= (size_t)(cols + K - 1) * 3 && out_pitch >= (size_t)cols * 3 * sizeof(int32_t), "pitch");
     CK(launch_conv(in, in_pitch, rows, cols, K, taps, norm, out, out_pitch, 0, g.sm_count, st));
     return OMPIMG_OK;
 }
@@ -520,18 +523,21 @@ extern "C" int ompimg_conv_u8_dev(const uint8_t *in, size_t in_pitch, int rows, 
     INIT(); STREAM(stream, st);
     NEED(in && out && taps && rows > 0 && cols > 0, "image");
     NEED(K >= 1 && K <= 15 && norm != 0, "K in 1..15, norm != 0");
+    NEED(in_pitch >= (size_t)(cols + K - 1) * 3 && out_pitch >= (size_t)cols * 3, "pitch");
     CK(launch_conv(in, in_pitch, rows, cols, K, taps, norm, out, out_pitch, 1, g.sm_count, st));
     return OMPIMG_OK;
 }
 extern "C" int ompimg_channel_sums_dev(const uint8_t *rgb, size_t pitch, int rows, int cols, unsigned long long *sums3, int stream) {
     INIT(); STREAM(stream, st);
     NEED(rgb && sums3 && rows > 0 && cols > 0, "image");
+    NEED(pitch >= (size_t)cols * 3, "pitch");
     CK(launch_channel_sums(rgb, pitch, rows, cols, sums3, g.sm_count, st));
     return OMPIMG_OK;
 }
 extern "C" int ompimg_gray_avg3_dev(const uint8_t *rgb, size_t ip, uint8_t *out, size_t op, int rows, int cols, int *min_max, int stream) {
     INIT(); STREAM(stream, st);
     NEED(rgb && out && min_max && rows > 0 && cols > 0, "image");
+    NEED(ip >= (size_t)cols * 3 && op >= (size_t)cols * 3, "pitch");
     CK(launch_gray_avg3(rgb, ip, out, op, rows, cols, min_max, g.sm_count, st));
     return OMPIMG_OK;
 }
@@ -624,9 +630,117 @@ extern "C" int ompimg_gray_inplace_host(uint8_t *data, int w, int h, int ch) {
     return OMPIMG_OK;
 }
 
-// a2 through host memory.  The device copies are pitched (pitch % 128 == 0) so that any width takes
-// the bulk-copy kernel; only the interior of dst travels back, which is what keeps the caller's
-// border bytes untouched.  Row bands (with their halo rows) go through the streams independently.
+namespace {
+// -------------------------------------------------------------------------------------------------
+// The row-band pipeline every other host entry point runs on.
+//
+// The image is cut into bands of rows.  Band i's input rows go up on ONE upload stream (the H2D engine is busy without
+// gaps; bands upload DISJOINT rows -- a band that needs halo rows waits for its neighbour's upload event instead of
+// uploading them a second time, so no two copies ever write the same device bytes); its kernel runs on one of three
+// compute streams as soon as the last row it needs has arrived; its result comes back on that compute stream (the D2H
+// engine, in parallel with the uploads).  Pageable caller memory is staged through two rings of pinned chunks: the
+// host thread (plus the copy pool) fills chunk i+1 while the DMA engines move chunk i, and empties result chunks as
+// their bands complete.  Pinned caller memory (ompimg_host_alloc, OMPIMG_PIN=register) skips both rings.
+// -------------------------------------------------------------------------------------------------
+struct BandPipe {
+    int nb = 0;                                  // bands
+    // input: dense host rows -> pitched device rows; band i uploads rows [in_r0(i), in_r0(i+1))
+    const uint8_t *h_in = nullptr; size_t in_row = 0; uint8_t *d_in = nullptr; size_t d_in_pitch = 0;
+    std::function<int(int)> in_r0;               // defined for 0..nb (in_r0(nb) = number of input rows)
+    std::function<int(int)> needs;               // kernel(i) may start when the upload of band needs(i) has completed
+    std::function<int(int, cudaStream_t)> launch;
+    // output: pitched device rows -> dense host rows; band i returns rows [out_r0(i), out_r0(i+1)), bytes [x_off, x_off+x_bytes) of each
+    uint8_t *h_out = nullptr; size_t out_row = 0; const uint8_t *d_out = nullptr; size_t d_out_pitch = 0;
+    size_t x_off = 0, x_bytes = 0;
+    std::function<int(int)> out_r0;
+};
+constexpr int PIPE_RING = 4, PIPE_COMPUTE_STREAMS = 3;
+
+int run_band_pipe(const BandPipe &bp) {
+    const int nb = bp.nb;
+    const bool has_out = bp.h_out != nullptr;
+    const bool in_direct = is_pinned(bp.h_in), out_direct = !has_out || is_pinned(bp.h_out);
+    size_t max_in = 0, max_out = 0;
+    for (int i = 0; i < nb; ++i) {
+        max_in = std::max(max_in, (size_t)(bp.in_r0(i + 1) - bp.in_r0(i)) * bp.in_row);
+        if (has_out) max_out = std::max(max_out, (size_t)(bp.out_r0(i + 1) - bp.out_r0(i)) * bp.out_row);
+    }
+    max_in = round_up(max_in, 4096); max_out = round_up(max_out, 4096);
+    if (!in_direct) RESERVE_PIN(g.pin[0], PIPE_RING * max_in);
+    if (!out_direct) RESERVE_PIN(g.pin[1], PIPE_RING * max_out);
+    int rc = need_events(2 * (size_t)nb);
+    if (rc) return rc;
+    cudaStream_t up = g.streams[OMPIMG_NUM_STREAMS - 1];
+    auto up_ev = [&](int i) { return g.chunk_events[i]; };
+    auto done_ev = [&](int i) { return g.chunk_events[nb + i]; };
+    auto drain = [&](int j) -> int {
+        CK(cudaEventSynchronize(done_ev(j)));
+        if (has_out && !out_direct) {
+            const int r0 = bp.out_r0(j), r1 = bp.out_r0(j + 1);
+            const uint8_t *slot = (const uint8_t *)g.pin[1].p + (size_t)(j % PIPE_RING) * max_out;
+            if (bp.x_off == 0 && bp.x_bytes == bp.out_row) g_copy.copy(bp.h_out + (size_t)r0 * bp.out_row, slot, (size_t)(r1 - r0) * bp.out_row);
+            else for (int r = r0; r < r1; ++r) memcpy(bp.h_out + (size_t)r * bp.out_row + bp.x_off, slot + (size_t)(r - r0) * bp.out_row + bp.x_off, bp.x_bytes);
+        }
+        return OMPIMG_OK;
+    };
+    auto issue = [&](int j) -> int {
+        cudaStream_t st = g.streams[j % PIPE_COMPUTE_STREAMS];
+        CK(cudaStreamWaitEvent(st, up_ev(bp.needs(j)), 0));
+        int r = bp.launch(j, st);
+        if (r) return r;
+        if (has_out) {
+            const int r0 = bp.out_r0(j), r1 = bp.out_r0(j + 1);
+            if (r1 > r0) {
+                uint8_t *dst = out_direct ? bp.h_out + (size_t)r0 * bp.out_row : (uint8_t *)g.pin[1].p + (size_t)(j % PIPE_RING) * max_out;
+                CK(cudaMemcpy2DAsync(dst + bp.x_off, bp.out_row, bp.d_out + (size_t)r0 * bp.d_out_pitch + bp.x_off, bp.d_out_pitch, bp.x_bytes, r1 - r0,
+                                     cudaMemcpyDeviceToHost, st));
+            }
+        }
+        CK(cudaEventRecord(done_ev(j), st));
+        return OMPIMG_OK;
+    };
+    int next_launch = 0, next_drain = 0;
+    for (int i = 0; i < nb; ++i) {
+        // ring slot i % RING (input and output) is free once band i-RING has come back
+        while (next_drain <= i - PIPE_RING) {
+            if (next_drain >= next_launch) return fail(OMPIMG_ERR_ARG, "band pipeline: halo deeper than the staging ring");
+            rc = drain(next_drain++);
+            if (rc) return rc;
+        }
+        const int r0 = bp.in_r0(i), r1 = bp.in_r0(i + 1);
+        if (r1 > r0) {
+            const uint8_t *src = bp.h_in + (size_t)r0 * bp.in_row;
+            if (!in_direct) {
+                uint8_t *slot = (uint8_t *)g.pin[0].p + (size_t)(i % PIPE_RING) * max_in;
+                g_copy.copy(slot, src, (size_t)(r1 - r0) * bp.in_row);
+                src = slot;
+            }
+            CK(cudaMemcpy2DAsync(bp.d_in + (size_t)r0 * bp.d_in_pitch, bp.d_in_pitch, src, bp.in_row, bp.in_row, r1 - r0, cudaMemcpyHostToDevice, up));
+        }
+        CK(cudaEventRecord(up_ev(i), up));
+        while (next_launch < nb && bp.needs(next_launch) <= i) {
+            rc = issue(next_launch++);
+            if (rc) return rc;
+        }
+    }
+    while (next_launch < nb) { rc = issue(next_launch++); if (rc) return rc; }
+    while (next_drain < nb) { rc = drain(next_drain++); if (rc) return rc; }
+    return OMPIMG_OK;
+}
+
+// bands of about STAGE_CHUNK bytes, at least `min_rows` rows (the halo depth), at most 64 bands
+int band_rows_for(size_t row_bytes, int rows, int min_rows) {
+    long long per = (long long)(STAGE_CHUNK / (row_bytes ? row_bytes : 1));
+    if (per < min_rows) per = min_rows;
+    if (per < 1) per = 1;
+    if ((rows + per - 1) / per > 64) per = (rows + 63) / 64;
+    return (int)per;
+}
+
+}  // namespace
+
+// a2 through host memory.  The device copies are pitched (pitch % 128 == 0) so that any width takes the tensor-map
+// kernel; only the interior of dst travels back, which is what keeps the caller's border bytes untouched.
 extern "C" int ompimg_sobel_host(const uint8_t *src, uint8_t *dst, int w, int h) {
     INIT();
     std::lock_guard<std::recursive_mutex> lk(g.mu);
@@ -634,45 +748,27 @@ extern "C" int ompimg_sobel_host(const uint8_t *src, uint8_t *dst, int w, int h)
     if (w < 3 || h < 3) return OMPIMG_OK;              // sobel.c:11-12: no interior, nothing written
     const size_t pitch = round_up((size_t)w, 128), plane = (size_t)w * h;
     ScopedPin pin_s(src, plane), pin_d(dst, plane);
-    const bool src_direct = is_pinned(src), dst_direct = is_pinned(dst);
     RESERVE(g.scratch[0], pitch * h + 256);
     RESERVE(g.scratch[1], pitch * h + 256);
     uint8_t *ds = (uint8_t *)g.scratch[0].p, *dd = (uint8_t *)g.scratch[1].p;
-    const uint8_t *hs = src;
-    uint8_t *hd = dst;
-    if (!src_direct) { RESERVE_PIN(g.pin[0], plane); hs = (const uint8_t *)g.pin[0].p; }
-    if (!dst_direct) { RESERVE_PIN(g.pin[1], plane); hd = (uint8_t *)g.pin[1].p; }
-    const int interior = h - 2;
-    int nb = (int)(plane / STAGE_CHUNK);
-    if (nb < 1) nb = 1;
-    if (nb > 32) nb = 32;
-    const int rows_per = (interior + nb - 1) / nb;
-    nb = (interior + rows_per - 1) / rows_per;
-    int rc = need_events(nb);
-    if (rc) return rc;
-    int i = 0;
-    for (int y0 = 1; y0 < h - 1; y0 += rows_per, ++i) {
-        const int y1 = y0 + rows_per < h - 1 ? y0 + rows_per : h - 1;   // output rows [y0, y1)
-        cudaStream_t st = g.streams[i % STAGE_STREAMS];
-        const int r0 = y0 - 1, nr = y1 - y0 + 2;                          // source rows incl. halo
-        if (!src_direct) g_copy.copy((uint8_t *)g.pin[0].p + (size_t)r0 * w, src + (size_t)r0 * w, (size_t)nr * w);
-        CK(cudaMemcpy2DAsync(ds + (size_t)r0 * pitch, pitch, hs + (size_t)r0 * w, w, w, nr, cudaMemcpyHostToDevice, st));
-        rc = sobel_common(ds + (size_t)r0 * pitch, pitch, 1, dd + (size_t)r0 * pitch, pitch, w, nr, 1, 0, 0, nullptr, nullptr, st);
-        if (rc) return rc;
-        CK(cudaMemcpy2DAsync(hd + (size_t)y0 * w + 1, w, dd + (size_t)y0 * pitch + 1, pitch, w - 2, y1 - y0, cudaMemcpyDeviceToHost, st));
-        CK(cudaEventRecord(g.chunk_events[i], st));
-    }
-    i = 0;
-    for (int y0 = 1; y0 < h - 1; y0 += rows_per, ++i) {
-        const int y1 = y0 + rows_per < h - 1 ? y0 + rows_per : h - 1;
-        CK(cudaEventSynchronize(g.chunk_events[i]));
-        if (!dst_direct)
-            for (int y = y0; y < y1; ++y) memcpy(dst + (size_t)y * w + 1, hd + (size_t)y * w + 1, (size_t)w - 2);
-    }
-    return OMPIMG_OK;
+    const int per = band_rows_for((size_t)w, h - 2, 2), nb = (h - 2 + per - 1) / per;
+    auto y0 = [=](int i) { return i >= nb ? h - 1 : 1 + i * per; };            // output rows of band i: [y0(i), y0(i+1))
+    BandPipe bp;
+    bp.nb = nb;
+    bp.h_in = src; bp.in_row = (size_t)w; bp.d_in = ds; bp.d_in_pitch = pitch;
+    bp.in_r0 = [=](int i) { return i == 0 ? 0 : i >= nb ? h : y0(i); };         // disjoint: band 0 also carries row 0, the last band row h-1
+    bp.needs = [=](int i) { return i + 1 < nb ? i + 1 : nb - 1; };              // the row below the band's last output row is the next band's first
+    bp.launch = [=](int i, cudaStream_t st) {
+        const int r0 = y0(i) - 1, nr = y0(i + 1) - y0(i) + 2;
+        return sobel_common(ds + (size_t)r0 * pitch, pitch, 1, dd + (size_t)r0 * pitch, pitch, w, nr, 1, 0, 0, nullptr, nullptr, st);
+    };
+    bp.h_out = dst; bp.out_row = (size_t)w; bp.d_out = dd; bp.d_out_pitch = pitch; bp.x_off = 1; bp.x_bytes = (size_t)w - 2;
+    bp.out_r0 = y0;
+    return run_band_pipe(bp);
 }
 
-// a5 through host memory: one iteration of main_with_sobel.c:51-74 on the caller's image.
+// a5 through host memory: one iteration of main_with_sobel.c:51-74 on the caller's image.  On the device the pass is
+// NOT in place (source image, edge plane and result image are three buffers), so the bands are independent.
 extern "C" int ompimg_gray_sobel_pass_host(uint8_t *img, int w, int h, int ch, uint8_t *edge) {
     INIT();
     std::lock_guard<std::recursive_mutex> lk(g.mu);
@@ -680,48 +776,48 @@ extern "C" int ompimg_gray_sobel_pass_host(uint8_t *img, int w, int h, int ch, u
     NEED(ch == 3 || ch == 4, "channels must be 3 or 4");
     const size_t row = (size_t)w * ch, ipitch = round_up(row, 128), epitch = round_up((size_t)w, 128);
     ScopedPin pin_i(img, row * h);
-    const bool direct = is_pinned(img);
     RESERVE(g.scratch[0], ipitch * h + 256);
     RESERVE(g.scratch[1], epitch * h + 256);
-    uint8_t *di = (uint8_t *)g.scratch[0].p, *de = (uint8_t *)g.scratch[1].p;
-    uint8_t *hi = img;
-    if (!direct) { RESERVE_PIN(g.pin[0], row * h); hi = (uint8_t *)g.pin[0].p; }
-    cudaStream_t st = g.streams[0];
-    // the scratch plane's border survives the pass (main_with_sobel.c:37): only a non-zero border has to travel
+    RESERVE(g.scratch[3], ipitch * h + 256);
+    uint8_t *di = (uint8_t *)g.scratch[0].p, *de = (uint8_t *)g.scratch[1].p, *dr = (uint8_t *)g.scratch[3].p;
+    cudaStream_t up = g.streams[OMPIMG_NUM_STREAMS - 1];
+    // the scratch plane's border survives the pass (main_with_sobel.c:37) and is what the image border becomes (:65-73):
+    // only a non-zero border has to travel.  Either way it is in place before the first band's upload event.
     bool zero_border = true;
     if (edge) {
         for (int x = 0; x < w && zero_border; ++x) zero_border = !edge[x] && !edge[(size_t)(h - 1) * w + x];
         for (int y = 0; y < h && zero_border; ++y) zero_border = !edge[(size_t)y * w] && !edge[(size_t)y * w + w - 1];
     }
-    if (zero_border) CK(cudaMemsetAsync(de, 0, epitch * h, st));
-    else CK(cudaMemcpy2DAsync(de, epitch, edge, w, w, h, cudaMemcpyHostToDevice, st));
-    int rows_per = (int)(STAGE_CHUNK / row);
-    if (rows_per < 1) rows_per = 1;
-    const int nb = (h + rows_per - 1) / rows_per;
-    int rc = need_events(nb);
+    if (zero_border) CK(cudaMemsetAsync(de, 0, epitch * h, up));
+    else CK(cudaMemcpy2DAsync(de, epitch, edge, w, w, h, cudaMemcpyHostToDevice, up));
+    if (ch == 4) CK(cudaMemsetAsync(dr, 0, ipitch * h, up));      // (alpha comes from the source image below; keeps the buffer defined)
+    const int per = band_rows_for(row, h, 2), nb = (h + per - 1) / per;
+    auto y0 = [=](int i) { return i >= nb ? h : i * per; };
+    BandPipe bp;
+    bp.nb = nb;
+    bp.h_in = img; bp.in_row = row; bp.d_in = di; bp.d_in_pitch = ipitch;
+    bp.in_r0 = y0;
+    bp.needs = [=](int i) { return i + 1 < nb ? i + 1 : nb - 1; };
+    bp.launch = [=](int i, cudaStream_t st) -> int {
+        const int a = y0(i), b = y0(i + 1);
+        const int r0 = a > 0 ? a - 1 : 0, r1 = b < h ? b + 1 : h;                 // source rows incl. halo
+        if (r1 - r0 >= 3) {
+            int rc = sobel_common(di + (size_t)r0 * ipitch, ipitch, ch, de + (size_t)r0 * epitch, epitch, w, r1 - r0, 1, 0, 0, nullptr, nullptr, st);
+            if (rc) return rc;
+        }
+        if (ch == 4) CK(cudaMemcpy2DAsync(dr + (size_t)a * ipitch, ipitch, di + (size_t)a * ipitch, ipitch, row, b - a, cudaMemcpyDeviceToDevice, st));   // alpha
+        CK(launch_replicate(de + (size_t)a * epitch, epitch, dr + (size_t)a * ipitch, ipitch, ch, w, b - a, 1, 0, 0, g.sm_count, st));
+        return OMPIMG_OK;
+    };
+    bp.h_out = img; bp.out_row = row; bp.d_out = dr; bp.d_out_pitch = ipitch; bp.x_off = 0; bp.x_bytes = row;
+    bp.out_r0 = y0;
+    int rc = run_band_pipe(bp);
     if (rc) return rc;
-    for (int y0 = 0; y0 < h; y0 += rows_per) {
-        const int nr = y0 + rows_per < h ? rows_per : h - y0;
-        if (!direct) g_copy.copy(hi + (size_t)y0 * row, img + (size_t)y0 * row, (size_t)nr * row);
-        CK(cudaMemcpy2DAsync(di + (size_t)y0 * ipitch, ipitch, hi + (size_t)y0 * row, row, row, nr, cudaMemcpyHostToDevice, st));
+    if (edge) {
+        // the driver's scratch plane ends the pass holding the edge values (border untouched)
+        CK(cudaMemcpy2DAsync(edge, w, de, epitch, w, h, cudaMemcpyDeviceToHost, g.streams[0]));
+        CK(cudaStreamSynchronize(g.streams[0]));
     }
-    rc = sobel_common(di, ipitch, ch, de, epitch, w, h, 1, 0, 0, nullptr, nullptr, st);
-    if (rc) return rc;
-    CK(launch_replicate(de, epitch, di, ipitch, ch, w, h, 1, 0, 0, g.sm_count, st));
-    int i = 0;
-    for (int y0 = 0; y0 < h; y0 += rows_per, ++i) {
-        const int nr = y0 + rows_per < h ? rows_per : h - y0;
-        CK(cudaMemcpy2DAsync(hi + (size_t)y0 * row, row, di + (size_t)y0 * ipitch, ipitch, row, nr, cudaMemcpyDeviceToHost, st));
-        CK(cudaEventRecord(g.chunk_events[i], st));
-    }
-    if (edge) CK(cudaMemcpy2DAsync(edge, w, de, epitch, w, h, cudaMemcpyDeviceToHost, st));
-    i = 0;
-    for (int y0 = 0; y0 < h; y0 += rows_per, ++i) {
-        const int nr = y0 + rows_per < h ? rows_per : h - y0;
-        CK(cudaEventSynchronize(g.chunk_events[i]));
-        if (!direct) g_copy.copy(img + (size_t)y0 * row, hi + (size_t)y0 * row, (size_t)nr * row);
-    }
-    CK(cudaStreamSynchronize(st));
     return OMPIMG_OK;
 }
 
@@ -758,38 +854,86 @@ extern "C" int ompimg_rgb_to_edge_batch_host(const uint8_t *rgb, size_t rgb_stri
     return OMPIMG_OK;
 }
 
+namespace {
+// out = (prior + sum) / norm with C division: the reference ACCUMULATES onto the caller's array before dividing
+// (old/parallel_convolution.c:17,20); prior == nullptr is the zeroed array every caller of the reference passes.
+int conv_host_common(const uint8_t *in_padded, int rows, int cols, int K, const int32_t *taps, int32_t norm, int32_t *out, bool accumulate) {
+    NEED(in_padded && out && taps && rows > 0 && cols > 0, "image");
+    NEED(K >= 1 && K <= 15 && norm != 0, "K in 1..15, norm != 0");
+    const size_t in_row = (size_t)(cols + K - 1) * 3;
+    const int in_rows = rows + K - 1;
+    const size_t in_pitch = round_up(in_row, 128);                 // aligned rows: the dp4a kernels load 32-bit words
+    const size_t out_row = (size_t)cols * 3 * sizeof(int32_t), out_pitch = round_up(out_row, 128);
+    RESERVE(g.scratch[0], in_pitch * in_rows + 256);
+    RESERVE(g.scratch[1], out_pitch * rows + 256);
+    uint8_t *din = (uint8_t *)g.scratch[0].p, *dout = (uint8_t *)g.scratch[1].p;
+    uint8_t *dprior = nullptr;
+    if (accumulate) {
+        RESERVE(g.scratch[4], out_pitch * rows + 256);
+        dprior = (uint8_t *)g.scratch[4].p;
+        CK(cudaMemcpy2DAsync(dprior, out_pitch, out, out_row, out_row, rows, cudaMemcpyHostToDevice, g.streams[OMPIMG_NUM_STREAMS - 1]));
+    }
+    const int per = band_rows_for(out_row, rows, K), nb = (rows + per - 1) / per;
+    auto y0 = [=](int i) { return i >= nb ? rows : i * per; };
+    BandPipe bp;
+    bp.nb = nb;
+    bp.h_in = in_padded; bp.in_row = in_row; bp.d_in = din; bp.d_in_pitch = in_pitch;
+    bp.in_r0 = [=](int i) { return i >= nb ? in_rows : i * per; };            // the last band also carries the K-1 pad rows
+    bp.needs = [=](int i) { return i + 1 < nb ? i + 1 : nb - 1; };            // per >= K: the K-1 rows below the band are in the next band's upload
+    bp.launch = [=](int i, cudaStream_t st) -> int {
+        const int a = y0(i), n = y0(i + 1) - a;
+        if (!accumulate) {
+            CK(launch_conv(din + (size_t)a * in_pitch, in_pitch, n, cols, K, taps, norm, dout + (size_t)a * out_pitch, out_pitch, 0, g.sm_count, st));
+        } else {
+            CK(launch_conv(din + (size_t)a * in_pitch, in_pitch, n, cols, K, taps, 1, dout + (size_t)a * out_pitch, out_pitch, 0, g.sm_count, st));
+            CK(launch_accum_div((int32_t *)(dout + (size_t)a * out_pitch), out_pitch, (const int32_t *)(dprior + (size_t)a * out_pitch), out_pitch, n, cols * 3, norm,
+                                g.sm_count, st));
+        }
+        return OMPIMG_OK;
+    };
+    bp.h_out = (uint8_t *)out; bp.out_row = out_row; bp.d_out = dout; bp.d_out_pitch = out_pitch; bp.x_off = 0; bp.x_bytes = out_row;
+    bp.out_r0 = y0;
+    return run_band_pipe(bp);
+}
+}  // namespace
+
 extern "C" int ompimg_conv_i32_host(const uint8_t *in_padded, int rows, int cols, int K, const int32_t *taps, int32_t norm, int32_t *out) {
     INIT();
     std::lock_guard<std::recursive_mutex> lk(g.mu);
-    NEED(in_padded && out && taps && rows > 0 && cols > 0, "image");
-    NEED(K >= 1 && K <= 15 && norm != 0, "K in 1..15, norm != 0");
-    const size_t in_row = (size_t)(cols + K - 1) * 3, in_rows = (size_t)rows + K - 1;
-    const size_t in_pitch = round_up(in_row, 128);                 // aligned rows: the dp4a kernel loads 32-bit words
-    const size_t out_row = (size_t)cols * 3 * sizeof(int32_t), out_pitch = round_up(out_row, 128), out_bytes = out_pitch * rows;
-    RESERVE(g.scratch[0], in_pitch * in_rows + 256);
-    RESERVE(g.scratch[1], out_bytes + 256);
-    cudaStream_t st = g.streams[0];
-    CK(cudaMemcpy2DAsync(g.scratch[0].p, in_pitch, in_padded, in_row, in_row, in_rows, cudaMemcpyHostToDevice, st));
-    CK(launch_conv((const uint8_t *)g.scratch[0].p, in_pitch, rows, cols, K, taps, norm, g.scratch[1].p, out_pitch, 0, g.sm_count, st));
-    CK(cudaMemcpy2DAsync(out, out_row, g.scratch[1].p, out_pitch, out_row, rows, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    return OMPIMG_OK;
+    return conv_host_common(in_padded, rows, cols, K, taps, norm, out, false);
+}
+extern "C" int ompimg_conv_i32_accum_host(const uint8_t *in_padded, int rows, int cols, int K, const int32_t *taps, int32_t norm, int32_t *out_inout) {
+    INIT();
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    return conv_host_common(in_padded, rows, cols, K, taps, norm, out_inout, true);
 }
 
 extern "C" int ompimg_avg_pixel_host(const uint8_t *rgb, int rows, int cols, long long *avgs) {
     INIT();
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     NEED(rgb && avgs && rows > 0 && cols > 0, "image");
-    const size_t bytes = (size_t)rows * cols * 3;
-    RESERVE(g.scratch[0], bytes + 256);
+    const size_t row = (size_t)cols * 3, pitch = round_up(row, 128);
+    RESERVE(g.scratch[0], pitch * rows + 256);
     RESERVE(g.scratch[2], 64);
-    cudaStream_t st = g.streams[0];
+    uint8_t *d = (uint8_t *)g.scratch[0].p;
+    unsigned long long *dsums = (unsigned long long *)g.scratch[2].p;
+    CK(cudaMemsetAsync(dsums, 0, 24, g.streams[OMPIMG_NUM_STREAMS - 1]));       // ordered before every band's upload event
+    const int per = band_rows_for(row, rows, 1), nb = (rows + per - 1) / per;
+    auto y0 = [=](int i) { return i >= nb ? rows : i * per; };
+    BandPipe bp;
+    bp.nb = nb;
+    bp.h_in = rgb; bp.in_row = row; bp.d_in = d; bp.d_in_pitch = pitch;
+    bp.in_r0 = y0;
+    bp.needs = [](int i) { return i; };
+    bp.launch = [=](int i, cudaStream_t st) -> int {
+        CK(launch_channel_sums(d + (size_t)y0(i) * pitch, pitch, y0(i + 1) - y0(i), cols, dsums, g.sm_count, st));     // partial sums add up atomically
+        return OMPIMG_OK;
+    };
+    int rc = run_band_pipe(bp);
+    if (rc) return rc;
     unsigned long long sums[3] = {0, 0, 0};
-    CK(cudaMemsetAsync(g.scratch[2].p, 0, 24, st));
-    CK(cudaMemcpyAsync(g.scratch[0].p, rgb, bytes, cudaMemcpyHostToDevice, st));
-    CK(launch_channel_sums((const uint8_t *)g.scratch[0].p, (size_t)cols * 3, rows, cols, (unsigned long long *)g.scratch[2].p, g.sm_count, st));
-    CK(cudaMemcpyAsync(sums, g.scratch[2].p, 24, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(cudaMemcpyAsync(sums, dsums, 24, cudaMemcpyDeviceToHost, g.streams[0]));
+    CK(cudaStreamSynchronize(g.streams[0]));
     // old/parallel_avg_pixel.c: every channel is summed three times (:19-23), added onto avgs (:28-30)
     // and divided by rows*cols*3 (:8,:40)
     const long long count = (long long)rows * cols * 3;
@@ -801,19 +945,31 @@ extern "C" int ompimg_gray_avg3_host(const uint8_t *rgb, uint8_t *out, int rows,
     INIT();
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     NEED(rgb && out && min_max && rows > 0 && cols > 0, "image");
-    const size_t bytes = (size_t)rows * cols * 3;
-    RESERVE(g.scratch[0], bytes + 256);
-    RESERVE(g.scratch[1], bytes + 256);
+    const size_t row = (size_t)cols * 3, pitch = round_up(row, 128);
+    RESERVE(g.scratch[0], pitch * rows + 256);
+    RESERVE(g.scratch[1], pitch * rows + 256);
     RESERVE(g.scratch[2], 64);
-    cudaStream_t st = g.streams[0];
+    uint8_t *d = (uint8_t *)g.scratch[0].p, *o = (uint8_t *)g.scratch[1].p;
+    int *dmm = (int *)g.scratch[2].p;
     const int init[2] = {256, -1};      // old/parallel_to_grayscale.c:9-10
-    CK(cudaMemcpyAsync(g.scratch[2].p, init, sizeof init, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(g.scratch[0].p, rgb, bytes, cudaMemcpyHostToDevice, st));
-    CK(launch_gray_avg3((const uint8_t *)g.scratch[0].p, (size_t)cols * 3, (uint8_t *)g.scratch[1].p, (size_t)cols * 3, rows, cols,
-                        (int *)g.scratch[2].p, g.sm_count, st));
-    CK(cudaMemcpyAsync(out, g.scratch[1].p, bytes, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(min_max, g.scratch[2].p, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(cudaMemcpyAsync(dmm, init, sizeof init, cudaMemcpyHostToDevice, g.streams[OMPIMG_NUM_STREAMS - 1]));
+    const int per = band_rows_for(row, rows, 1), nb = (rows + per - 1) / per;
+    auto y0 = [=](int i) { return i >= nb ? rows : i * per; };
+    BandPipe bp;
+    bp.nb = nb;
+    bp.h_in = rgb; bp.in_row = row; bp.d_in = d; bp.d_in_pitch = pitch;
+    bp.in_r0 = y0;
+    bp.needs = [](int i) { return i; };
+    bp.launch = [=](int i, cudaStream_t st) -> int {
+        CK(launch_gray_avg3(d + (size_t)y0(i) * pitch, pitch, o + (size_t)y0(i) * pitch, pitch, y0(i + 1) - y0(i), cols, dmm, g.sm_count, st));   // min/max combine atomically
+        return OMPIMG_OK;
+    };
+    bp.h_out = out; bp.out_row = row; bp.d_out = o; bp.d_out_pitch = pitch; bp.x_off = 0; bp.x_bytes = row;
+    bp.out_r0 = y0;
+    int rc = run_band_pipe(bp);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(min_max, dmm, 8, cudaMemcpyDeviceToHost, g.streams[0]));
+    CK(cudaStreamSynchronize(g.streams[0]));
     return OMPIMG_OK;
 }
 
@@ -827,6 +983,15 @@ static void die(const char *fn) {
 // monolithic/include/parallel_to_grayscale.h:4
 extern "C" void convert_to_grayscale(unsigned char *data, int width, int height, int channels) {
     if (width <= 0 || height <= 0) return;              // the reference's loop body never runs
+    if (channels == 1 || channels == 2) {
+        // Undefined behaviour in the reference (parallel_to_grayscale.c:10-14 reads and writes p[0..2] of EVERY pixel: out
+        // of bounds at the end of the buffer and racing between threads), which in practice exits 0 and writes some PNG.
+        // There is no defined result to reproduce, and aborting would turn such uploads into HTTP 500s: the image is
+        // left as it is -- a grayscale input is already gray -- with one line on stderr.  ("channels".)
+        static bool warned = false;
+        if (!warned) { fprintf(stderr, "libompimg_b200: convert_to_grayscale: channels=%d is undefined behaviour in the reference; image left unchanged\n", channels); warned = true; }
+        return;
+    }
     if (!g.ready && data && (channels == 3 || channels == 4)) {
         // persistent worker mode (worker.cu): OMPIMG_WORKER names the process that holds the CUDA context
         const char *m = getenv("OMPIMG_LUMA");

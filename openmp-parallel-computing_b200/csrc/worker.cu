@@ -9,6 +9,12 @@
 // below) and read the result back.  The CLI contract above the boundary (argv, stdout, exit code)
 // is untouched.  Still no CPU path: an unreachable worker means this process initialises CUDA itself.
 //
+// Trust model: the worker serves local processes of its own user (socket mode 0600, peer credentials checked with
+// SO_PEERCRED; OMPIMG_WORKER_SOCKET_MODE / OMPIMG_WORKER_ALLOW_UIDS widen that deliberately).  A request can neither
+// crash nor starve it: shared mappings must be size-sealed memfds (F_SEAL_SHRINK|F_SEAL_GROW, so no SIGBUS by
+// truncation), mappings and payloads are capped (OMPIMG_WORKER_MAX_BYTES, default 1 GiB), nothing is pre-faulted, and
+// a pooled result buffer never carries another client's bytes back (Sobel's untouched border is zeroed).
+//
 // Wire format (host byte order, one machine): request header, payload; reply header, payload.  The payload normally
 // does not cross the socket: the client keeps a memfd mapping, passes the descriptor once (SCM_RIGHTS) and both sides
 // work in that shared memory (socket copies cost ~8 ms per 6 MB image each way; a memcpy into the mapping 0.5 ms).
@@ -21,6 +27,7 @@
 #include <thread>
 #include <vector>
 
+#include <fcntl.h>
 #include <signal.h>
 #include <sys/mman.h>
 #include <sys/socket.h>
@@ -89,8 +96,13 @@ bool shm_reserve(size_t n) {
     if (g_shm) { munmap(g_shm, g_shm_cap); g_shm = nullptr; g_shm_cap = 0; }
     if (g_shm_fd >= 0) { ::close(g_shm_fd); g_shm_fd = -1; }
     const size_t want = (n + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
-    const int fd = memfd_create("ompimg_b200", MFD_CLOEXEC);
-    if (fd < 0 || ftruncate(fd, (off_t)want) != 0) { if (fd >= 0) ::close(fd); g_shm_off = true; return false; }
+    // sealed against resizing: the worker refuses a mapping whose size could change under it
+    const int fd = memfd_create("ompimg_b200", MFD_CLOEXEC | MFD_ALLOW_SEALING);
+    if (fd < 0 || ftruncate(fd, (off_t)want) != 0 || fcntl(fd, F_ADD_SEALS, F_SEAL_SHRINK | F_SEAL_GROW) != 0) {
+        if (fd >= 0) ::close(fd);
+        g_shm_off = true;
+        return false;
+    }
     void *m = mmap(nullptr, want, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
     if (m == MAP_FAILED) { ::close(fd); g_shm_off = true; return false; }
     g_shm_fd = fd; g_shm = static_cast<uint8_t *>(m); g_shm_cap = want; g_shm_sent = false;
@@ -241,6 +253,46 @@ void pool_give(PinBuf b) {
     g_pool.push_back(b);
 }
 
+uint64_t max_request_bytes() {
+    static uint64_t v = 0;
+    if (!v) {
+        const char *e = getenv("OMPIMG_WORKER_MAX_BYTES");
+        v = e ? strtoull(e, nullptr, 0) : 0;
+        if (!v) v = 1ull << 30;                    // 1 GiB: a 16384 x 16384 RGBA image
+    }
+    return v;
+}
+// may this peer use the worker?  default: the worker's own user (and root); OMPIMG_WORKER_ALLOW_UIDS="1000,33" or "*" widens it
+bool peer_allowed(int fd) {
+    ucred cr{};
+    socklen_t len = sizeof cr;
+    if (getsockopt(fd, SOL_SOCKET, SO_PEERCRED, &cr, &len) != 0) return false;
+    if (cr.uid == geteuid() || cr.uid == 0) return true;
+    const char *e = getenv("OMPIMG_WORKER_ALLOW_UIDS");
+    if (!e) return false;
+    if (!strcmp(e, "*")) return true;
+    for (const char *q = e; *q;) {                 // comma-separated decimal uids
+        char *end;
+        const unsigned long u = strtoul(q, &end, 10);
+        if (end == q) break;
+        if (u == cr.uid) return true;
+        q = *end == ',' ? end + 1 : end;
+    }
+    return false;
+}
+// a descriptor a client passed: map it only if it is a memfd whose size is sealed and within the cap
+bool map_client_memfd(int fd, uint8_t **map, size_t *len) {
+    struct stat st{};
+    const int seals = fcntl(fd, F_GET_SEALS);
+    if (seals < 0 || (seals & (F_SEAL_SHRINK | F_SEAL_GROW)) != (F_SEAL_SHRINK | F_SEAL_GROW)) return false;
+    if (fstat(fd, &st) != 0 || st.st_size <= 0 || (uint64_t)st.st_size > 2 * max_request_bytes() + 8192) return false;
+    void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    if (m == MAP_FAILED) return false;
+    *map = static_cast<uint8_t *>(m);
+    *len = (size_t)st.st_size;
+    return true;
+}
+
 void reply_error(int fd, int status, const char *msg) {
     WkReply rp{};
     rp.magic = WK_MAGIC; rp.status = status; rp.nbytes = 0;
@@ -258,18 +310,15 @@ void serve_connection(int fd) {
         if (!recv_header(fd, &rq, sizeof rq, &newfd)) break;
         if (newfd >= 0) {
             if (map) { munmap(map, map_len); map = nullptr; map_len = 0; }
-            struct stat st{};
-            if (fstat(newfd, &st) == 0 && st.st_size > 0) {
-                void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_POPULATE, newfd, 0);
-                if (m != MAP_FAILED) { map = static_cast<uint8_t *>(m); map_len = (size_t)st.st_size; }
-            }
+            const bool mapped = map_client_memfd(newfd, &map, &map_len);
             ::close(newfd);
+            if (!mapped) { reply_error(fd, OMPIMG_ERR_ARG, "shared mapping refused: it must be a memfd sealed with F_SEAL_SHRINK|F_SEAL_GROW, within the size cap"); break; }
         }
         if (rq.magic != WK_MAGIC) break;
         const long long px = (long long)rq.width * rq.height;
         const uint64_t want = rq.op == WK_GRAY ? (uint64_t)px * (uint64_t)rq.channels : rq.op == WK_SOBEL ? (uint64_t)px : 0;
         if (rq.op == WK_PING) { WkReply rp{}; rp.magic = WK_MAGIC; if (!write_full(fd, &rp, sizeof rp)) break; continue; }
-        if (rq.width <= 0 || rq.height <= 0 || rq.nbytes != want || (rq.op != WK_GRAY && rq.op != WK_SOBEL) || rq.nbytes > (1ull << 36)) {
+        if (rq.width <= 0 || rq.height <= 0 || rq.nbytes != want || (rq.op != WK_GRAY && rq.op != WK_SOBEL) || rq.nbytes > max_request_bytes()) {
             reply_error(fd, OMPIMG_ERR_ARG, "malformed request");
             break;
         }
@@ -287,6 +336,13 @@ void serve_connection(int fd) {
             if (!read_full(fd, in.p, rq.nbytes)) break;
             src = static_cast<uint8_t *>(in.p);
             dst = rq.op == WK_SOBEL ? static_cast<uint8_t *>(out.p) : src;
+            if (rq.op == WK_SOBEL) {
+                // sobel_edge never writes the border and the pooled plane held an earlier client's result: zero the border
+                const size_t w = (size_t)rq.width, h = (size_t)rq.height;
+                memset(dst, 0, w);
+                memset(dst + (h - 1) * w, 0, w);
+                for (size_t y = 1; y + 1 < h; ++y) dst[y * w] = dst[y * w + w - 1] = 0;
+            }
         }
         int rc;
         {
@@ -324,11 +380,24 @@ extern "C" int ompimg_worker_serve(const char *socket_path, int device) {
     a.sun_family = AF_UNIX;
     if (strlen(socket_path) >= sizeof a.sun_path) return OMPIMG_ERR_ARG;
     strcpy(a.sun_path, socket_path);
-    ::unlink(socket_path);
+    {
+        // a path left behind by a dead worker is removed; a path another worker still answers on is not stolen
+        const int probe = ::socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
+        if (probe >= 0) {
+            const bool live = ::connect(probe, reinterpret_cast<sockaddr *>(&a), sizeof a) == 0;
+            ::close(probe);
+            if (live) { fprintf(stderr, "ompimg_worker: %s is served by another worker\n", socket_path); return OMPIMG_ERR_ARG; }
+        }
+        struct stat st{};
+        if (lstat(socket_path, &st) == 0 && S_ISSOCK(st.st_mode)) ::unlink(socket_path);
+    }
     const int ls = ::socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
     if (ls < 0) return OMPIMG_ERR_ARG;
-    if (::bind(ls, reinterpret_cast<sockaddr *>(&a), sizeof a) != 0 || ::listen(ls, 64) != 0) { ::close(ls); return OMPIMG_ERR_ARG; }
-    ::chmod(socket_path, 0666);
+    const mode_t old_umask = umask(0177);          // the socket is born 0600: no window in which it is world-connectable
+    const bool bound = ::bind(ls, reinterpret_cast<sockaddr *>(&a), sizeof a) == 0 && ::listen(ls, 64) == 0;
+    umask(old_umask);
+    if (!bound) { ::close(ls); return OMPIMG_ERR_ARG; }
+    if (const char *m = getenv("OMPIMG_WORKER_SOCKET_MODE")) ::chmod(socket_path, (mode_t)(strtoul(m, nullptr, 8) & 0777));
     // warm the pipelines and the pinned pool once so that the first request pays neither module loading nor page-locking
     {
         PinBuf a, b;
@@ -355,6 +424,7 @@ extern "C" int ompimg_worker_serve(const char *socket_path, int device) {
     for (;;) {
         const int fd = ::accept4(ls, nullptr, nullptr, SOCK_CLOEXEC);
         if (fd < 0) { if (errno == EINTR) continue; break; }
+        if (!peer_allowed(fd)) { reply_error(fd, OMPIMG_ERR_ARG, "peer uid not allowed (OMPIMG_WORKER_ALLOW_UIDS)"); ::close(fd); continue; }
         std::thread([fd, device] { ompimg_init(device); serve_connection(fd); }).detach();
     }
     ::close(ls);

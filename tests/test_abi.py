@@ -84,3 +84,17 @@ def test_reference_drivers_link_against_the_library(tmp_path, pkg):
                         "-lompimg_b200", f"-Wl,-rpath,{pkg.LIB_PATH.parent}", "-lm"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_integration_makefiles_build_the_reference_drivers(tmp_path, pkg):
+    """integration/Makefile and integration/Makefile_with_sobel (the corrected replacement for the reference's broken
+    monolithic/Makefile_with_sobel:11) build the reference's UNMODIFIED drivers against the library."""
+    ref = Path("/root/reference/monolithic")
+    if not (ref / "src" / "main_with_sobel.c").exists():
+        pytest.skip("the reference tree is not on this box")
+    for mk, exe in (("Makefile", "grayscale"), ("Makefile_with_sobel", "grayscale_sobel")):
+        r = subprocess.run(["make", "-C", str(ref), "-f", str(ROOT / "integration" / mk), f"BIN_DIR={tmp_path}", f"B200={pkg.LIB_PATH.parent}"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        syms = subprocess.run(["nm", "-D", "--undefined-only", str(tmp_path / exe)], capture_output=True, text=True, check=True).stdout
+        assert "convert_to_grayscale" in syms and ("sobel_edge" in syms) == (exe == "grayscale_sobel")

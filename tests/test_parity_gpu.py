@@ -417,6 +417,111 @@ def test_old_kernels_golden(gpu, O, golden, key):
     assert sha(g3.astype(np.int64)) == e["gray3_sha256_i64"] and mm.tolist() == e["minmax"]
 
 
+@pytest.mark.parametrize("key", ["37_53_5_273", "24_31_3_16"])
+def test_old_signatures_through_long_array_adapters(gpu, O, key, tmp_path):
+    """The reference's old/ functions and tests/adapters/old_long_adapters.c (same `long`-array signatures, on the C ABI)
+    called with the SAME arguments: identical `long` arrays -- including the accumulate-onto-the-caller's-array statement
+    (old/parallel_convolution.c:17) with a non-zero array, and avgs that do not start at zero (old/parallel_avg_pixel.c:28-30)."""
+    import ctypes as C
+    import subprocess
+    from common import ROOT
+    rows, cols, K, norm = map(int, key.split("_"))
+    so = tmp_path / f"adapters_{key}.so"
+    lib_dir = gpu.LIB_PATH.parent
+    r = subprocess.run(["gcc", "-O2", "-fPIC", "-shared", f"-I{ROOT / 'oracle' / 'stub'}", f"-I{ROOT / 'include'}",
+                        f"-DDIM_ROW={rows}", f"-DDIM_COL={cols}", f"-DDIM_KERNEL={K}", f"-DGBLUR_NORM={norm}",
+                        str(ROOT / "tests" / "adapters" / "old_long_adapters.c"), "-o", str(so), f"-L{lib_dir}", "-lompimg_b200", f"-Wl,-rpath,{lib_dir}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ours = O.RefOld.__new__(O.RefOld)
+    ours.rows, ours.cols, ours.K, ours.norm, ours.L = rows, cols, K, norm, C.CDLL(str(so))
+    rng = np.random.default_rng(rows * 7 + K)
+    padded = O.synth((rows + K - 1) * (cols + K - 1) * 3, 0xAD00 + K).reshape(rows + K - 1, cols + K - 1, 3).astype(np.int64)
+    kern = rng.integers(-5, 9, (K, K)).astype(np.int64)
+    prior = rng.integers(-100000, 100000, (rows, cols, 3)).astype(np.int64)
+    want = O.convolution_long(padded, kern, norm, prior.copy())
+    if O.have_ref_old(rows, cols, K, norm):
+        assert np.array_equal(O.RefOld(rows, cols, K, norm).convolution(padded, kern, prior.copy()), want)
+    assert np.array_equal(ours.convolution(padded, kern, prior.copy()), want)
+    assert np.array_equal(ours.convolution(padded, kern, np.zeros_like(prior)), O.convolution_long(padded, kern, norm, np.zeros_like(prior)))
+    img = np.ascontiguousarray(padded[:rows, :cols])
+    assert ours.avg_pixel(img, (5, 1000003, -77)).tolist() == O.avg_pixel_long(img, (5, 1000003, -77)).tolist()
+    g3, mm = ours.gray_avg3(img)
+    w3, wmm = O.gray_avg3_long(img)
+    assert np.array_equal(g3, w3) and mm.tolist() == wmm.tolist()
+
+
+def test_convolution_accumulate_and_argument_checks(gpu, O):
+    rows, cols, K = 70, 333, 5
+    padded = O.synth((rows + K - 1) * (cols + K - 1) * 3, 77).reshape(rows + K - 1, cols + K - 1, 3)
+    kern = np.outer([1, 4, 6, 4, 1], [1, 4, 6, 4, 1]).astype(np.int64)
+    prior = np.random.default_rng(3).integers(-(1 << 20), 1 << 20, (rows, cols, 3)).astype(np.int32)
+    want = O.convolution_long(padded.astype(np.int64), kern, 256, prior.astype(np.int64))
+    assert np.array_equal(gpu.parallel_convolution(padded, kern, 256, out=prior.copy()), want)
+    L = gpu.lib()
+    src = to_dev_pitched(gpu, padded.reshape(rows + K - 1, -1), (cols + K - 1) * 3 + 1)
+    dst = gpu.DeviceBuffer(rows * cols * 3 * 4)
+    taps = np.ascontiguousarray(kern, np.int32)
+    # uint8 output never clamps (neither does the reference): it is the low byte of the exact result, documented in the header
+    assert L.ompimg_conv_u8_dev(src.ptr, (cols + K - 1) * 3 + 1, rows, cols, K, taps.ctypes.data, 100, dst.ptr, cols * 3, 0) == 0
+    gpu.sync(0)
+    assert np.array_equal(dst.download(rows * cols * 3).reshape(rows, cols, 3), O.convolution_u8(padded, kern, 100).astype(np.uint8))
+    # pitches that cannot hold a row: refused instead of read/written out of bounds
+    assert L.ompimg_conv_i32_dev(src.ptr, (cols + K - 1) * 3 - 1, rows, cols, K, taps.ctypes.data, 256, dst.ptr, cols * 12, 0) == -2
+    assert L.ompimg_conv_i32_dev(src.ptr, (cols + K - 1) * 3 + 1, rows, cols, K, taps.ctypes.data, 256, dst.ptr, cols * 12 - 4, 0) == -2
+    assert L.ompimg_channel_sums_dev(src.ptr, cols * 3 - 1, rows, cols, dst.ptr, 0) == -2
+    for bad in (np.zeros((8, 8), np.uint8), np.zeros((8, 8, 4), np.uint8)):
+        with pytest.raises(ValueError):
+            gpu.parallel_avg_pixel(bad)
+        with pytest.raises(ValueError):
+            gpu.parallel_to_grayscale(bad)
+        with pytest.raises(ValueError):
+            gpu.parallel_convolution(bad, np.ones((3, 3)), 9)
+
+
+def test_frozen_grayscale_leaves_one_and_two_channel_images_alone(gpu):
+    """channels 1 / 2 are undefined behaviour in the reference (parallel_to_grayscale.c:10-14); the drop-in neither aborts
+    (the services would answer 500) nor invents pixels: the buffer is left as it is."""
+    import ctypes as C
+    for ch in (1, 2):
+        a = np.random.default_rng(ch).integers(0, 256, (16, 24, ch), dtype=np.uint8)
+        b = a.copy()
+        gpu.lib().convert_to_grayscale(C.c_void_p(b.ctypes.data), 24, 16, ch)
+        assert np.array_equal(a, b)
+        with pytest.raises(gpu.OmpimgError):
+            gpu.convert_to_grayscale(b)                      # the non-frozen API still reports it
+
+
+def test_host_pipelines_many_bands(gpu, O):
+    """the row-band host pipeline with many bands, pageable and pinned buffers, odd widths (ring reuse, halo events)"""
+    h, w = 1500, 2037
+    rng = np.random.default_rng(11)
+    plane = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    pre = np.full((h, w), 0x3C, np.uint8)
+    assert np.array_equal(gpu.sobel_edge(plane, pre.copy()), O.sobel(plane, pre.copy()))
+    rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    edge = np.zeros((h, w), np.uint8); edge[0, :] = 9; edge[:, -1] = 200
+    want_img, want_edge = O.gray_sobel_pass(rgb.copy(), edge.copy())
+    got_img, got_edge = gpu.gray_sobel_pass(rgb.copy(), edge.copy())
+    assert np.array_equal(got_img, want_img) and np.array_equal(got_edge, want_edge)
+    rgba = rng.integers(0, 256, (700, 1001, 4), dtype=np.uint8)
+    assert np.array_equal(gpu.gray_sobel_pass(rgba.copy())[0], O.gray_sobel_pass(rgba.copy())[0])
+    pin = gpu.PinnedBuffer(h * w * 3)
+    pimg = pin.array.reshape(h, w, 3)
+    pimg[:] = rgb
+    assert np.array_equal(gpu.gray_sobel_pass(pimg)[0], O.gray_sobel_pass(rgb.copy())[0])
+    pin.free()
+    K = 9
+    padded = rng.integers(0, 256, (900 + K - 1, 1111 + K - 1, 3), dtype=np.uint8)
+    kern = rng.integers(-3, 4, (K, K)).astype(np.int64)
+    assert np.array_equal(gpu.parallel_convolution(padded, kern, 7), O.convolution_u8(padded, kern, 7))
+    big = rng.integers(0, 256, (3000, 1999, 3), dtype=np.uint8)
+    assert gpu.parallel_avg_pixel(big, (3, 2, 1)).tolist() == O.avg_pixel_u8(big, (3, 2, 1)).tolist()
+    g3, mm = gpu.parallel_to_grayscale(big)
+    w3, wmm = O.gray_avg3_u8(big)
+    assert np.array_equal(g3, w3) and mm.tolist() == wmm.tolist()
+
+
 @pytest.mark.parametrize("K,kind", [(3, "rand"), (5, "box"), (5, "gauss"), (5, "rand"), (7, "rand"), (9, "box"), (9, "gauss"), (9, "rand"),
                                     (4, "rand"), (11, "box"), (2, "rand"), (1, "rand")])
 def test_convolution_vs_oracle(gpu, O, K, kind):

@@ -248,3 +248,81 @@ def test_real_worker_serves_concurrent_clients(O, real_worker):
             img = O.gray_inplace(img, ch)
         want_edge = O.sobel(np.ascontiguousarray(img[:, :, 0]), np.full((37, 53), 0xAB, np.uint8))
         assert out.split()[:2] == [sha(img), sha(want_edge)], i
+
+
+# ------------------------------------------------------------------------------------------------ hardening
+def test_client_mapping_is_size_sealed(O, tmp_path):
+    """The client's memfd must be sealed against resizing (the worker refuses anything else): a truncation after the
+    worker's bounds check would otherwise SIGBUS the shared worker."""
+    import fcntl
+    seen = []
+
+    class SealWorker(FakeWorker):
+        def serve(self, c):
+            with c:
+                hdr, fds, _, _ = socket.recv_fds(c, REQ.size, 4)
+                if fds:
+                    seen.append(fcntl.fcntl(fds[0], fcntl.F_GET_SEALS))
+                    try:
+                        os.ftruncate(fds[0], 4096)                  # a sealed memfd cannot be resized by anyone
+                        seen.append("truncated")
+                    except OSError:
+                        seen.append("sealed")
+                c.sendall(REP.pack(MAGIC, -3, 0, b"stop"))
+
+    fw = SealWorker(O, tmp_path / "w.sock")
+    try:
+        run_client(tmp_path / "w.sock", 3, 1)
+    finally:
+        fw.close()
+    assert seen and isinstance(seen[0], int)
+    want = fcntl.F_SEAL_SHRINK | fcntl.F_SEAL_GROW
+    assert seen[0] & want == want and seen[1] == "sealed"
+
+
+def _raw_request(sock_path, header, payload=b"", fd=None):
+    c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    c.settimeout(30)
+    c.connect(str(sock_path))
+    with c:
+        if fd is not None:
+            socket.send_fds(c, [header], [fd])
+        else:
+            c.sendall(header)
+        if payload:
+            c.sendall(payload)
+        rep = recv_full(c, REP.size)
+        if rep is None:
+            return None, None
+        magic, status, n, msg = REP.unpack(rep)
+        body = recv_full(c, n) if n and status == 0 and fd is None else b""
+        return status, (msg.rstrip(b"\0").decode(), body)
+
+
+@pytest.mark.gpu
+def test_real_worker_refuses_what_could_hurt_it(O, real_worker):
+    assert oct(os.stat(real_worker).st_mode & 0o777) == "0o600"                 # born private
+    # (1) an unsealed memfd: refused before it is mapped
+    fd = os.memfd_create("evil", os.MFD_CLOEXEC)
+    os.ftruncate(fd, 1 << 20)
+    st, (msg, _) = _raw_request(real_worker, REQ.pack(MAGIC, 1, 16, 16, 3, 0, WK_SHM | WK_NEWFD, 0, 16 * 16 * 3), fd=fd)
+    os.close(fd)
+    assert st == -2 and "sealed" in msg
+    # (2) a payload beyond the cap: refused before anything is allocated
+    st, (msg, _) = _raw_request(real_worker, REQ.pack(MAGIC, 1, 65536, 65536, 4, 0, 0, 0, 65536 * 65536 * 4))
+    assert st == -2
+    # (3) the worker is still alive and a pooled Sobel plane comes back with a ZERO border, not an earlier client's bytes
+    h, w = 40, 64
+    noise = np.random.default_rng(1).integers(1, 256, (h, w), dtype=np.uint8)
+    for plane in (noise, np.zeros((h, w), np.uint8)):
+        st, (msg, body) = _raw_request(real_worker, REQ.pack(MAGIC, 2, w, h, 1, 0, 0, 0, w * h), plane.tobytes())
+        assert st == 0, msg
+        got = np.frombuffer(body, np.uint8).reshape(h, w)
+        assert np.array_equal(got, O.sobel(plane, np.zeros((h, w), np.uint8)))
+
+
+@pytest.mark.gpu
+def test_second_worker_does_not_steal_a_live_socket(real_worker):
+    r = subprocess.run([str(WORKER), "--socket", str(real_worker)], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "another worker" in r.stderr
+    assert run_client(real_worker, 3, 1).returncode == 0                       # the first worker still serves
