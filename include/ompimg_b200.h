@@ -126,9 +126,12 @@ OMPIMG_API int ompimg_rgb_to_edge_band_dev(const uint8_t *rgb, size_t rgb_pitch,
 OMPIMG_API int ompimg_replicate_dev(const uint8_t *plane, size_t plane_pitch, uint8_t *img, size_t img_pitch,
                          int channels, int width, int height, int nframes,
                          size_t plane_stride, size_t img_stride, int stream);
-/* one iteration of the driver loop, in place on img; edge is the driver's persistent w*h
- * scratch plane (main_with_sobel.c:37): its border bytes are preserved and copied into the
- * image border exactly as the reference does.  edge == NULL means a zero border. */
+/* one iteration of the driver loop (main_with_sobel.c:51-74), in place on img.  edge is the driver's persistent w*h scratch
+ * plane (main_with_sobel.c:37): its border bytes are what the image border becomes, exactly as in the reference; edge == NULL
+ * means a zero border.  3-channel images whose rows are 16-byte friendly take the fused path: a small preparation kernel and
+ * ONE kernel that reads RGB and writes the replicated edge value back (6 bytes/pixel; the edge plane's interior is then
+ * NOT written -- the plane never exists).  Other layouts run the fused gray->Sobel kernel into `edge` and a replicate
+ * kernel (edge must then be given).  The host form always returns the edge plane in `edge` when it is not NULL. */
 OMPIMG_API int ompimg_gray_sobel_pass_dev(uint8_t *img, size_t img_pitch, int channels, uint8_t *edge, size_t edge_pitch,
                                int width, int height, int nframes, size_t img_stride, size_t edge_stride, int stream);
 OMPIMG_API int ompimg_gray_sobel_pass_host(uint8_t *img, int width, int height, int channels, uint8_t *edge);

@@ -56,6 +56,13 @@ struct StencilArgs {
     int no_bias;                 // 1: MUFU.SQRT was validated exact on this device, skip the +0.5 guard (runtime.cu)
 };
 cudaError_t launch_sobel(const StencilArgs &a, int sm_count, cudaStream_t st);
+// a5 in place on 3-channel images (main_with_sobel.c:51-74 as a preparation kernel + one fused kernel that writes RGB):
+// scratch is device memory of rows_bytes + border_bytes + entries_bytes, private to the launch until it has completed
+struct PassScratch { size_t row_pitch, rows_bytes, border_bytes, entry_pitch, entries_bytes; size_t total() const { return rows_bytes + border_bytes + entries_bytes; } };
+bool pass_inplace_supported(const uint8_t *img, size_t pitch, size_t stride, int w, int h, int ch, int nframes);
+PassScratch pass_inplace_scratch(int w, int h, int nframes, int sm_count);
+cudaError_t launch_gray_sobel_pass_inplace(uint8_t *img, size_t pitch, size_t stride, int w, int h, int nframes, const uint8_t *edge, size_t epitch,
+                                           size_t estride, int fma_mode, int no_bias, uint8_t *scratch, int sm_count, cudaStream_t st);
 int sqrt_exact_flag();          // runtime.cu: 1 when the bound device passed the exhaustive MUFU.SQRT check
 cudaError_t launch_isqrt_selftest(uint8_t *out_dev, unsigned int count, float bias, cudaStream_t st);
 

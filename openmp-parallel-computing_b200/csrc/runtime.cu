@@ -46,6 +46,7 @@ struct Ctx {
     DevBuf scratch[5];                       // host-API staging on the device
     DevBuf slots[OMPIMG_NUM_STREAMS][2];     // per-stream (input, output) slots of the batch pipeline
     DevBuf pin[3];                           // pinned host staging for pageable caller buffers (grow-only)
+    DevBuf pass_scratch[OMPIMG_NUM_STREAMS]; // per stream: what the in-place gray+Sobel pass saves before it overwrites the image
     std::vector<cudaEvent_t> chunk_events;   // one per in-flight chunk of a staged download
     std::recursive_mutex mu;
 };
@@ -313,6 +314,7 @@ extern "C" int ompimg_shutdown(void) {
     for (auto &b : g.scratch) { if (b.p) cudaFree(b.p); b = DevBuf(); }
     for (auto &s : g.slots) for (auto &b : s) { if (b.p) cudaFree(b.p); b = DevBuf(); }
     for (auto &b : g.pin) { if (b.p) cudaFreeHost(b.p); b = DevBuf(); }
+    for (auto &b : g.pass_scratch) { if (b.p) cudaFree(b.p); b = DevBuf(); }
     for (auto e : g.chunk_events) cudaEventDestroy(e);
     g.chunk_events.clear();
     for (auto &t : g.timers) { if (t.a) cudaEventDestroy(t.a); if (t.b) cudaEventDestroy(t.b); }
@@ -502,8 +504,22 @@ extern "C" int ompimg_replicate_dev(const uint8_t *plane, size_t pp, uint8_t *im
 extern "C" int ompimg_gray_sobel_pass_dev(uint8_t *img, size_t ip, int ch, uint8_t *edge, size_t ep, int w, int h, int nframes,
                                           size_t is, size_t es, int stream) {
     INIT(); STREAM(stream, st);
-    NEED(img && edge && w > 0 && h > 0 && nframes > 0, "image");
+    NEED(img && w > 0 && h > 0 && nframes > 0, "image");
     NEED(ch == 3 || ch == 4, "channels must be 3 or 4");
+    NEED(ip >= (size_t)w * ch && (!edge || ep >= (size_t)w), "pitch");
+    if (w >= 3 && h >= 3 && pass_inplace_supported(img, ip, is, w, h, ch, nframes)) {
+        // 3 channels, 16-byte friendly layout: a preparation kernel saves what the in-place kernel could find overwritten,
+        // then ONE fused kernel reads RGB and writes the replicated edge value back over it (6 bytes/pixel moved).  The
+        // scratch plane's border bytes are read (they become the image border); its interior is not written -- no edge plane
+        // ever exists on this path.  The side buffers belong to the stream: passes on different streams do not share them.
+        std::lock_guard<std::recursive_mutex> lk(g.mu);
+        const PassScratch sz = pass_inplace_scratch(w, h, nframes, g.sm_count);
+        RESERVE(g.pass_scratch[stream], sz.total() + 256);
+        CK(launch_gray_sobel_pass_inplace(img, ip, is, w, h, nframes, edge, ep, es, g.luma_mode, g.sqrt_exact, (uint8_t *)g.pass_scratch[stream].p,
+                                          g.sm_count, st));
+        return OMPIMG_OK;
+    }
+    NEED(edge, "this layout (4 channels, or rows that are not 16-byte friendly) needs the scratch plane");
     int rc = sobel_common(img, ip, ch, edge, ep, w, h, nframes, is, es, nullptr, nullptr, st);
     if (rc) return rc;
     CK(launch_replicate(edge, ep, img, ip, ch, w, h, nframes, es, is, g.sm_count, st));

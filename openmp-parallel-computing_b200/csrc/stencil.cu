@@ -38,6 +38,15 @@ namespace ompimg {
 // fetches them with 1-D bulk copies (UBLKCP) straight over NVLink into two spare row slots, on the
 // same mbarrier as the stage they belong to, and the consumer reads those two rows from the spare
 // slots: the halo exchange is part of the kernel, there is no staging copy and no collective.
+//
+// In-place RGB output (MODE 2, ompimg_gray_sobel_pass_dev: one iteration of main_with_sobel.c:51-74 on the image itself).
+// The kernel writes the replicated edge value over the RGB pixels it read (a4 fused as an epilogue: 3 x 128-bit stores
+// per lane and row, 6 bytes/pixel moved instead of 8 with a separate replicate pass).  Being in place, a warp may
+// overwrite pixels another warp still has to read: the 16-byte halo blocks either side of its strip and the first and
+// last source row of its band.  pass_prepare_kernel therefore saves, before this kernel starts, (a) every band's first
+// and last source row and (b) the two pixels either side of every strip boundary of every row (16 bytes per boundary, with
+// the image-border values of the row in the outermost entries).  The kernel takes (a) into the spare row slots like
+// row-band mode does and (b) with one more 96-byte tensor box per stage, and never looks at the halo blocks of its stages.
 // ---------------------------------------------------------------------------------------------
 constexpr int TW_WARPS = 8;
 constexpr uint32_t round128(uint32_t v) { return (v + 127u) & ~127u; }
@@ -50,8 +59,19 @@ struct TmaGeom {
     static constexpr uint32_t HALFSTAGE = round128(3 * HS);
     static constexpr uint32_t STAGE = HAS_FULL && round128(3 * RS) > 2 * HALFSTAGE ? round128(3 * RS) : 2 * HALFSTAGE;
     static constexpr uint32_t HALO_SLOT = round128(HAS_FULL && RS > 2 * HS ? RS : 2 * HS);
-    static constexpr uint32_t warp_bytes(bool halo) { return S * STAGE + (halo ? 2 * HALO_SLOT : 0); }
-    static constexpr uint32_t smem(bool halo) { return TW_WARPS * (warp_bytes(halo) + 8 * S) + 128; }
+    // mode 0: plain; 1: row-band mode (two spare row slots); 2: in-place RGB output (spare row slots + a 128-byte side box per stage)
+    static constexpr uint32_t warp_bytes(int mode) { return S * STAGE + (mode ? 2 * HALO_SLOT : 0) + (mode == 2 ? S * 128 : 0); }
+    static constexpr uint32_t smem(int mode) { return TW_WARPS * (warp_bytes(mode) + 8 * S) + 128; }
+};
+
+// what pass_prepare_kernel saved for the in-place RGB pass (device memory owned by the caller of the launcher)
+struct PassSide {
+    const uint8_t *rows;            // [frame][band][2][row_pitch]: every band's first and last source row
+    size_t row_pitch;
+    const uint8_t *border;          // [frame][2][row_pitch]: what image rows 0 / height-1 become
+    const uint8_t *entries_base;    // [frame][row][entries] x 16 bytes: (pixel left of strip boundary k, pixel right of it, 8 unused), RGB in bytes 0..2 / 4..6
+    size_t entry_pitch;             // bytes per row of entries (multiple of 16)
+    int entries;                    // nstrips + 1
 };
 
 struct TmaStencilParams {
@@ -60,6 +80,11 @@ struct TmaStencilParams {
     uint8_t *dst;
     size_t dst_pitch, dst_stride;
     const uint8_t *halo_above, *halo_below;   // row-band mode: source rows -1 / height (or nullptr)
+    // in-place RGB output (MODE 2, see sobel_tma_kernel): what pass_prepare_kernel saved before anything is overwritten
+    CUtensorMap map_side;     // {nstrips+1 entries of 16 bytes, height, frames}: the two pixels either side of every strip boundary + border values; box = 2 entries x 3 rows
+    const uint8_t *side_rows; // [frame][band][first, last source row][side_row_pitch]
+    size_t side_row_pitch;
+    const uint8_t *border_rows;   // [frame][top, bottom][side_row_pitch]: what image rows 0 and height-1 become (scratch plane's border rows, replicated)
     int width, height;
     int nbands, rows_per_band, nstrips;
     int fold;                 // the last strip is at most 256 pixels wide: one warp takes it for two bands
@@ -161,12 +186,46 @@ __device__ __forceinline__ void sobel_step(const uint32_t (&P)[8], const uint32_
     }
 }
 
+// RGBOUT epilogue (main_with_sobel.c:65-73): 16 edge bytes -> 16 RGB pixels, three 128-bit stores
+__device__ __forceinline__ void store_rgb48(uint8_t *out, const uint4 &o) {
+    const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+    uint32_t r[12];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        r[3 * q] = prmt(w[q], w[q], 0x1000);
+        r[3 * q + 1] = prmt(w[q], w[q], 0x2211);
+        r[3 * q + 2] = prmt(w[q], w[q], 0x3332);
+    }
+    uint4 *d = reinterpret_cast<uint4 *>(out);
+    d[0] = make_uint4(r[0], r[1], r[2], r[3]);
+    d[1] = make_uint4(r[4], r[5], r[6], r[7]);
+    d[2] = make_uint4(r[8], r[9], r[10], r[11]);
+}
+// the group that straddles the end of a row whose width is not a multiple of 16: pixel by pixel (one lane per row)
+__device__ __forceinline__ void store_rgb_partial(uint8_t *out, const uint4 &o, int npx) {
+#pragma unroll 1
+    for (int j = 0; j < npx; ++j) {
+        const uint32_t w = j < 8 ? (j < 4 ? o.x : o.y) : (j < 12 ? o.z : o.w);
+        const uint8_t v = (uint8_t)(w >> (8 * (j & 3)));
+        out[3 * j] = v; out[3 * j + 1] = v; out[3 * j + 2] = v;
+    }
+}
+__device__ __forceinline__ void set_byte16(uint4 &o, int i, uint32_t v) {       // byte i (0..15) of the 16-byte group := v
+    const uint32_t sh = 8u * (uint32_t)(i & 3), m = ~(255u << sh), b = v << sh;
+    if (i < 4) o.x = (o.x & m) | b;
+    else if (i < 8) o.y = (o.y & m) | b;
+    else if (i < 12) o.z = (o.z & m) | b;
+    else o.w = (o.w & m) | b;
+}
+
 template <int N> struct IntC { static constexpr int value = N; };
 template <bool B> struct BoolC { static constexpr bool value = B; };
 
-template <int CH, int FMA_MODE, bool BIAS, bool HALO>
+template <int CH, int FMA_MODE, bool BIAS, int MODE>
 __global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? 3 : 2) sobel_tma_kernel(const __grid_constant__ TmaStencilParams p) {
     using G = TmaGeom<CH>;
+    constexpr bool HALO = MODE == 1, RGBOUT = MODE == 2, SUBST = MODE != 0;
+    static_assert(!RGBOUT || CH == 3, "in-place RGB output is built for 3 channels");
     constexpr int S = G::S;
     constexpr uint32_t RS = G::RS, HS = G::HS, STAGE = G::STAGE, HALFSTAGE = G::HALFSTAGE;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -198,9 +257,10 @@ __global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? 3 : 2) sobel_tma_kern
     const bool has_b = split && nin_b >= 3;
 
     const uint32_t base = (smem_u32(smem) + 127u) & ~127u;
-    const uint32_t ring0 = base + (uint32_t)warp * G::warp_bytes(HALO);
-    const uint32_t bar0 = base + TW_WARPS * G::warp_bytes(HALO) + (uint32_t)warp * (8 * S);
-    const uint32_t hslot0 = ring0 + S * STAGE;          // HALO: the two spare row slots (row -1, row height)
+    const uint32_t ring0 = base + (uint32_t)warp * G::warp_bytes(MODE);
+    const uint32_t bar0 = base + TW_WARPS * G::warp_bytes(MODE) + (uint32_t)warp * (8 * S);
+    const uint32_t hslot0 = ring0 + S * STAGE;          // SUBST: the two spare row slots (the band's first / last source row)
+    const uint32_t sbox0 = hslot0 + 2 * G::HALO_SLOT;   // RGBOUT: one 128-byte side box per stage (3 rows x 16 bytes used)
 
     if (lane == 0) {
 #pragma unroll
@@ -213,10 +273,13 @@ __global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? 3 : 2) sobel_tma_kern
     const int cxa = (xs * CH - 16) / 8;
     const int cxb = folded ? cxa : cxa + 256 * CH / 8;
     // row-band mode: which source rows of this band come from the neighbours, and where they sit in the trip sequence
-    const bool use_above = HALO && p.halo_above != nullptr && a0 < 0;
-    const bool use_below = HALO && p.halo_below != nullptr && a1 >= p.height;
-    const int below_i = p.height - a0;                  // index of source row `height` in the band's row sequence
+    // (in-place RGB output: EVERY band takes its first and last source row from the copies saved by pass_prepare_kernel)
+    const bool use_above = RGBOUT || (HALO && p.halo_above != nullptr && a0 < 0);
+    const bool use_below = RGBOUT || (HALO && p.halo_below != nullptr && a1 >= p.height);
+    const int below_i = RGBOUT ? nin_a - 1 : p.height - a0;      // index of that last row in the band's row sequence
     const int below_t = below_i / 3, below_rho = below_i - 3 * below_t;
+    const uint8_t *row_first = RGBOUT ? p.side_rows + ((size_t)frame * p.nbands + band_a) * 2 * p.side_row_pitch : p.halo_above;
+    const uint8_t *row_last = RGBOUT ? row_first + p.side_row_pitch : p.halo_below;
 
     // elected lane: one 1-D bulk copy per (half-)strip piece of a neighbour's row into a spare row slot
     auto peer_row_bytes = [&]() -> uint32_t {
@@ -241,10 +304,11 @@ __global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? 3 : 2) sobel_tma_kern
     auto request = [&](int s, int tt) {
         const uint32_t bar = bar0 + 8 * s, dst = ring0 + (uint32_t)s * STAGE;
         uint32_t tx = split ? (has_b ? 6u * HS : 3u * HS) : 3u * RS;
-        if (HALO) {
+        if (SUBST) {
             if (use_above && tt == 0) tx += peer_row_bytes();
             if (use_below && tt == below_t) tx += peer_row_bytes();
         }
+        if (RGBOUT) tx += 96u;
         mbar_expect_tx(bar, tx);
         if (G::HAS_FULL && !split) {
             tma_load_3d(dst, &p.map_full, cxa, a0 + 3 * tt, frame, bar);
@@ -252,10 +316,11 @@ __global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? 3 : 2) sobel_tma_kern
             tma_load_3d(dst, &p.map_half, cxa, a0 + 3 * tt, frame, bar);
             if (has_b) tma_load_3d(dst + HALFSTAGE, &p.map_half, cxb, b0 + 3 * tt, frame, bar);
         }
-        if (HALO) {
-            if (use_above && tt == 0) peer_row_copy(hslot0, p.halo_above, bar);
-            if (use_below && tt == below_t) peer_row_copy(hslot0 + G::HALO_SLOT, p.halo_below, bar);
+        if (SUBST) {
+            if (use_above && tt == 0) peer_row_copy(hslot0, row_first, bar);
+            if (use_below && tt == below_t) peer_row_copy(hslot0 + G::HALO_SLOT, row_last, bar);
         }
+        if (RGBOUT) tma_load_3d(sbox0 + (uint32_t)s * 128u, &p.map_side, 2 * strip, a0 + 3 * tt, frame, bar);      // entries strip, strip+1 of three rows (a box must START on a 16-byte boundary of global memory: hence 16-byte entries)
     };
     if (elect_one_sync()) {
         for (int t = 0; t < S && t < ntrips; ++t) request(t, t);
@@ -268,12 +333,15 @@ __global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? 3 : 2) sobel_tma_kern
     // x == width-1 (and possibly bytes past the row), 4 both.  Border groups must leave dst's border bytes as they are
     // (sobel.c:11-12 never writes them): a few narrow stores, in the few warps that hold such a group.  (Reading the group
     // back and merging was tried: the dependent load stalls those warps for a DRAM latency per row -- 0.75 -> 0.49.)
+    // (in-place RGB output writes the border pixels too -- they become the scratch plane's border values,
+    // main_with_sobel.c:65-73 -- so there every lane inside the image stores its whole group)
     int mode = 0;
     if (x0 < p.width && nin >= 3) {
         const bool l = x0 == 0, r = x0 + 16 > p.width - 1;
         mode = l ? (r ? 4 : 2) : (r ? 3 : 1);
     }
     const int plast = min(16, p.width - 1 - x0);
+    const int npx = min(16, p.width - x0);              // RGBOUT: pixels of the group inside the image
     const bool edge_warp = __any_sync(0xffffffffu, mode >= 2);       // warp-uniform
     const uint32_t rs = split ? HS : RS;                                  // bytes between the rows of a stage
     const uint32_t my = ring0 + (uint32_t)hb * HALFSTAGE + 16u + (uint32_t)lc * (16u * CH);
@@ -283,12 +351,14 @@ __global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? 3 : 2) sobel_tma_kern
     {
         const bool first = lc == 0, last = lc == (split ? 15 : 31);
         ec.edge_off = first ? -4 : 16 * CH;
-        ec.edge_sh = first ? 8u * (4u - CH) : 0u;
+        ec.edge_sh = first && !RGBOUT ? 8u * (4u - CH) : 0u;
         ec.mL = first ? 0xffffffffu : 0u;
         ec.mR = last ? 0xffffffffu : 0u;
     }
     const size_t dpitch = p.dst_pitch;
-    uint8_t *out = p.dst + (size_t)frame * p.dst_stride + ((ptrdiff_t)rin0 - 1) * (ptrdiff_t)p.dst_pitch + x0;   // stores go one row above the source row being consumed
+    uint8_t *out = p.dst + (size_t)frame * p.dst_stride + ((ptrdiff_t)rin0 - 1) * (ptrdiff_t)p.dst_pitch + (size_t)x0 * (RGBOUT ? 3 : 1);   // stores go one row above the source row being consumed
+    const uint32_t side_off = ec.mL ? 0u : 20u;         // RGBOUT: the strip-edge pixel of this lane in a side-box row (first lane: left one, last lane: right one)
+    uint32_t side_prev = 0;                             // ... and the previous row's, whose low byte is that row's border value in the outermost lanes
     float half = BIAS ? 0.5f : 0.0f;
     if (BIAS) asm volatile("" : "+f"(half));
 
@@ -303,12 +373,13 @@ __global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? 3 : 2) sobel_tma_kern
     auto row = [&](auto rho_c, auto checked_c, uint32_t addr, int t) {
         constexpr int RHO = decltype(rho_c)::value;
         constexpr bool CHECKED = decltype(checked_c)::value;
-        if (HALO && CHECKED) {
+        if (SUBST && CHECKED) {
             if (use_above && t == 0 && RHO == 0) addr = my_halo;
             if (use_below && t == below_t && RHO == below_rho) addr = my_halo + G::HALO_SLOT;
         }
         RowRaw<CH> raw;
         load_row<CH>(addr, ec.edge_off, raw);
+        if (RGBOUT) raw.e0 = lds32(sbox0 + (uint32_t)s * 128u + (uint32_t)RHO * 32u + side_off);      // the halo blocks of the stage may be overwritten already
         if (RHO == 2) {
             __syncwarp();                                   // every lane holds the stage's three rows
             if (elect_one_sync() && t + S < ntrips) request(s, t + S);
@@ -318,12 +389,26 @@ __global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? 3 : 2) sobel_tma_kern
         sobel_step<RHO>(P, Q, U, V, gx, gy);
         const bool emit = !CHECKED || (3 * t + RHO >= 2 && 3 * t + RHO < nin);       // the first two rows only prime the row state
         if (emit) {
-            const uint4 o = sobel_mag16(gx, gy, half);              // once per row, whatever the lanes' store modes
-            if (mode == 1) *reinterpret_cast<uint4 *>(out) = o;
-            if (edge_warp) {
-                if (mode >= 2) store_edge16(out, o, mode, plast);
+            uint4 o = sobel_mag16(gx, gy, half);                    // once per row, whatever the lanes' store modes
+            if (!RGBOUT) {
+                if (mode == 1) *reinterpret_cast<uint4 *>(out) = o;
+                if (edge_warp) {
+                    if (mode >= 2) store_edge16(out, o, mode, plast);
+                }
+            } else {
+                if (edge_warp) {
+                    // the image border takes the scratch plane's border values of the OUTPUT row (the previous source row's side entries)
+                    const uint32_t br = __shfl_sync(0xffffffffu, side_prev, 31) & 255u;
+                    if (mode == 2 || mode == 4) o.x = (o.x & 0xffffff00u) | (side_prev & 255u);
+                    if (mode >= 3) set_byte16(o, plast, br);
+                }
+                if (mode) {
+                    if (npx == 16) store_rgb48(out, o);
+                    else store_rgb_partial(out, o, npx);
+                }
             }
         }
+        if (RGBOUT) side_prev = raw.e0;
         out += dpitch;
     };
     auto trip = [&](auto checked_c, int t) {
@@ -335,9 +420,27 @@ __global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? 3 : 2) sobel_tma_kern
         if (++s == S) { s = 0; ph ^= 1; }
     };
 
+    if (RGBOUT) {
+        // image rows 0 and height-1 become the scratch plane's border rows: copied by the strips of the first / last band
+        // (nobody reads those rows of the image any more: bands take them from the saved copies)
+        const uint8_t *brow = p.border_rows + (size_t)frame * 2 * p.side_row_pitch + (size_t)x0 * 3;
+        uint8_t *irow = p.dst + (size_t)frame * p.dst_stride + (size_t)x0 * 3;
+        for (int which = 0; which < 2; ++which) {
+            if (which == 0 ? a0 != 0 : a1 != p.height - 1) continue;
+            const uint8_t *sr = brow + (size_t)which * p.side_row_pitch;
+            uint8_t *dr = irow + (size_t)(which ? p.height - 1 : 0) * p.dst_pitch;
+            if (npx == 16) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) reinterpret_cast<uint4 *>(dr)[q] = reinterpret_cast<const uint4 *>(sr)[q];
+            } else {
+                for (int j = 0; j < 3 * npx; ++j) dr[j] = sr[j];
+            }
+        }
+    }
+
     // trips [1, tsteady) lie entirely inside every storing lane's band and hold no substituted row
     int tsteady = (has_b ? min(nin_a, nin_b) : nin_a) / 3;
-    if (HALO && use_below) tsteady = min(tsteady, below_t);
+    if (SUBST && use_below) tsteady = min(tsteady, below_t);
     trip(BoolC<true>{}, 0);
     int t = 1;
     for (; t < tsteady; ++t) trip(BoolC<false>{}, t);
@@ -374,35 +477,43 @@ static cudaError_t make_row_map(CUtensorMap *m, const uint8_t *base, uint32_t ro
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-template <int CH, int FMA_MODE, bool BIAS, bool HALO>
-static cudaError_t launch_sobel_tma_h(const StencilArgs &a, int sm_count, cudaStream_t st) {
-    using G = TmaGeom<CH>;
-    TmaStencilParams p{};
-    p.dst = a.dst; p.dst_pitch = a.dst_pitch; p.dst_stride = a.dst_stride;
-    p.width = a.width; p.height = a.height;
-    p.halo_above = a.halo_above; p.halo_below = a.halo_below;
-    p.nstrips = (a.width + 511) / 512;
-    p.row_bytes16 = (uint32_t)(((size_t)a.width * CH + 15) & ~(size_t)15);
+// band / strip decomposition of a launch (shared by the kernel launch and by the in-place pass's preparation)
+struct TmaDecomp { int nstrips, rows_per_band, nbands; };
+static TmaDecomp tma_decomp(int width, int height, int nframes, int ch, int sm_count) {
+    TmaDecomp d;
+    d.nstrips = (width + 511) / 512;
     // Band height (1 mod 3: each band then consumes a multiple of three source rows), chosen to waste least: every band
     // re-reads two rows and primes on two rows (2/rows extra), and a launch of T tasks on the resident warp slots
     // (24 per SM for planes, 16 for RGB(A)) runs in ceil(T/slots) waves of which the last is only partly full.
     int rpb = 130;
-    {
-        const double slots = (double)sm_count * (CH == 1 ? 24 : 16);
-        double best = -1.0;
-        for (int c = 130; c >= 16; c -= 3) {
-            const double tasks = (double)a.nframes * p.nstrips * ((a.height - 1 + c - 1) / c);
-            const double waves = tasks / slots, full = waves <= 1.0 ? 1.0 : (double)(long long)(waves + 0.999999);
-            const double eff = waves / full * (double)c / (double)(c + 2);
-            if (eff > best * 1.005) { best = eff; rpb = c; }        // ties go to the taller band
-        }
+    const double slots = (double)sm_count * (ch == 1 ? 24 : 16);
+    double best = -1.0;
+    for (int c = 130; c >= 16; c -= 3) {
+        const double tasks = (double)nframes * d.nstrips * ((height - 1 + c - 1) / c);
+        const double waves = tasks / slots, full = waves <= 1.0 ? 1.0 : (double)(long long)(waves + 0.999999);
+        const double eff = waves / full * (double)c / (double)(c + 2);
+        if (eff > best * 1.005) { best = eff; rpb = c; }        // ties go to the taller band
     }
     { static int env = -1; if (env < 0) { const char *e = getenv("OMPIMG_SOBEL_BAND"); env = e ? atoi(e) : 0; } if (env > 0) rpb = env; }
-    p.rows_per_band = rpb;
-    p.nbands = max(1, (a.height - 1 + rpb - 1) / rpb);
+    d.rows_per_band = rpb;
+    d.nbands = max(1, (height - 1 + rpb - 1) / rpb);
+    return d;
+}
+
+template <int CH, int FMA_MODE, bool BIAS, int MODE>
+static cudaError_t launch_sobel_tma_h(const StencilArgs &a, int sm_count, cudaStream_t st, const PassSide *side = nullptr) {
+    using G = TmaGeom<CH>;
+    constexpr bool HALO = MODE == 1;
+    TmaStencilParams p{};
+    p.dst = a.dst; p.dst_pitch = a.dst_pitch; p.dst_stride = a.dst_stride;
+    p.width = a.width; p.height = a.height;
+    p.halo_above = a.halo_above; p.halo_below = a.halo_below;
+    const TmaDecomp dc = tma_decomp(a.width, a.height, a.nframes, CH, sm_count);
+    p.nstrips = dc.nstrips; p.rows_per_band = dc.rows_per_band; p.nbands = dc.nbands;
+    p.row_bytes16 = (uint32_t)(((size_t)a.width * CH + 15) & ~(size_t)15);
     // a last strip of at most 256 pixels (3840 = 7.5 strips) would leave half a warp idle: fold two bands into one warp
     { static int env = -1; if (env < 0) { const char *e = getenv("OMPIMG_SOBEL_FOLD"); env = e ? atoi(e) : 1; }
-      p.fold = env && p.nbands >= 2 && a.width - (p.nstrips - 1) * 512 <= 256 && !HALO; }
+      p.fold = env && p.nbands >= 2 && a.width - (p.nstrips - 1) * 512 <= 256 && MODE == 0; }
     p.tasks_per_frame = p.fold ? p.nbands * (p.nstrips - 1) + (p.nbands + 1) / 2 : p.nbands * p.nstrips;
     p.ntasks = (long long)a.nframes * p.tasks_per_frame;
     const long long ctas = (p.ntasks + TW_WARPS - 1) / TW_WARPS;
@@ -414,24 +525,144 @@ static cudaError_t launch_sobel_tma_h(const StencilArgs &a, int sm_count, cudaSt
     }
     e = make_row_map(&p.map_half, a.src, p.row_bytes16, a.src_pitch, a.height, a.nframes, a.src_stride, G::HS);
     if (e != cudaSuccess) return e;
-    constexpr int smem = (int)G::smem(HALO);
+    if (MODE == 2) {
+        if (!side) return cudaErrorInvalidValue;
+        p.side_rows = side->rows; p.side_row_pitch = side->row_pitch; p.border_rows = side->border;
+        EncodeTiledFn enc = encode_tiled_fn();
+        if (!enc) return cudaErrorNotSupported;
+        const cuuint64_t dims[3] = {(cuuint64_t)side->entries * 2, (cuuint64_t)a.height, (cuuint64_t)a.nframes};      // uint64 elements
+        const cuuint64_t strides[2] = {side->entry_pitch, side->entry_pitch * (size_t)a.height};
+        const cuuint32_t box[3] = {4, 3, 1}, estr[3] = {1, 1, 1};
+        if (enc(&p.map_side, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<uint8_t *>(side->entries_base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+    }
+    constexpr int smem = (int)G::smem(MODE);
     static unsigned long long attr_mask = 0;
     int dev = 0;
     e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (!(attr_mask >> dev & 1ULL)) {
-        e = cudaFuncSetAttribute(sobel_tma_kernel<CH, FMA_MODE, BIAS, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        e = cudaFuncSetAttribute(sobel_tma_kernel<CH, FMA_MODE, BIAS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         attr_mask |= 1ULL << dev;
     }
     count_launch();
-    sobel_tma_kernel<CH, FMA_MODE, BIAS, HALO><<<(unsigned)ctas, TW_WARPS * 32, smem, st>>>(p);
+    sobel_tma_kernel<CH, FMA_MODE, BIAS, MODE><<<(unsigned)ctas, TW_WARPS * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 template <int CH, int FMA_MODE, bool BIAS>
 static cudaError_t launch_sobel_tma_t(const StencilArgs &a, int sm_count, cudaStream_t st) {
-    return (a.halo_above || a.halo_below) ? launch_sobel_tma_h<CH, FMA_MODE, BIAS, true>(a, sm_count, st)
-                                          : launch_sobel_tma_h<CH, FMA_MODE, BIAS, false>(a, sm_count, st);
+    return (a.halo_above || a.halo_below) ? launch_sobel_tma_h<CH, FMA_MODE, BIAS, 1>(a, sm_count, st)
+                                          : launch_sobel_tma_h<CH, FMA_MODE, BIAS, 0>(a, sm_count, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The in-place pass (a5, ompimg_gray_sobel_pass_dev with 3 channels): pass_prepare_kernel, then sobel_tma_kernel<3,...,2>.
+// ---------------------------------------------------------------------------------------------
+struct PrepParams {
+    const uint8_t *img; size_t pitch, stride;
+    int w, h, nframes, nbands, rpb, nstrips;
+    uint32_t row_bytes16;
+    const uint8_t *edge; size_t epitch, estride;         // the driver's scratch plane (its border is what the image border becomes) or nullptr = zero
+    uint8_t *rows; size_t row_pitch;                     // out: [frame][band][2][row_pitch]
+    uint8_t *border; /* out: [frame][2][row_pitch] */
+    uint8_t *entries; size_t entry_pitch;                // out: [frame][row][nstrips+1] x 16 bytes
+};
+// Reads the image only; everything the in-place kernel could find overwritten is copied out first (see sobel_tma_kernel).
+__global__ void __launch_bounds__(256) pass_prepare_kernel(const PrepParams p) {
+    const long long chunks = p.row_bytes16 / 16;
+    const long long nA = (long long)p.nframes * p.nbands * 2 * chunks;          // band rows
+    const long long nC = (long long)p.nframes * 2 * chunks;                    // border rows (replicated)
+    const long long nB = (long long)p.nframes * p.h * (p.nstrips + 1);         // strip-boundary entries
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nA + nC + nB; i += (long long)gridDim.x * blockDim.x) {
+        if (i < nA) {
+            const long long c = i % chunks, q = i / chunks;
+            const int which = (int)(q & 1), b = (int)((q >> 1) % p.nbands);
+            const long long f = (q >> 1) / p.nbands;
+            const int a0 = b * p.rpb, yb = min(p.h, (b + 1) * p.rpb + 1), a1 = min(yb, p.h - 1);
+            if (a1 - a0 + 1 < 3) continue;                                      // a band without output rows is never consumed
+            const int r = which ? a1 : a0;
+            const uint4 v = *reinterpret_cast<const uint4 *>(p.img + f * p.stride + (size_t)r * p.pitch + c * 16);
+            *reinterpret_cast<uint4 *>(p.rows + (size_t)q * p.row_pitch + c * 16) = v;
+        } else if (i < nA + nC) {
+            const long long j = i - nA, c = j % chunks, q = j / chunks;          // q = frame*2 + which
+            const int which = (int)(q & 1);
+            const long long f = q >> 1;
+            uint32_t o[4] = {0, 0, 0, 0};
+            if (p.edge) {
+                const uint8_t *er = p.edge + f * p.estride + (size_t)(which ? p.h - 1 : 0) * p.epitch;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const long long byte = c * 16 + k;
+                    const uint32_t v = byte < (long long)p.w * 3 ? er[byte / 3] : 0u;
+                    o[k >> 2] |= v << (8 * (k & 3));
+                }
+            }
+            *reinterpret_cast<uint4 *>(p.border + (size_t)q * p.row_pitch + c * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+        } else {
+            const long long j = i - nA - nC;
+            const int k = (int)(j % (p.nstrips + 1));
+            const long long fy = j / (p.nstrips + 1), f = fy / p.h;
+            const int y = (int)(fy - f * p.h);
+            const uint8_t *row = p.img + f * p.stride + (size_t)y * p.pitch;
+            const uint8_t *er = p.edge ? p.edge + f * p.estride + (size_t)y * p.epitch : nullptr;
+            const int xb = k * 512;
+            uint32_t L, R;
+            if (k == 0) { const uint32_t bl = er ? er[0] : 0u; L = bl * 0x010101u; }
+            else { const uint8_t *q = row + (size_t)(xb - 1) * 3; L = q[0] | (q[1] << 8) | (q[2] << 16); }
+            if (xb < p.w) { const uint8_t *q = row + (size_t)xb * 3; R = q[0] | (q[1] << 8) | (q[2] << 16); }
+            else { const uint32_t br = er ? er[p.w - 1] : 0u; R = br * 0x010101u; }
+            *reinterpret_cast<uint4 *>(p.entries + (size_t)fy * p.entry_pitch + (size_t)k * 16) = make_uint4(L, R, 0u, 0u);
+        }
+    }
+}
+
+bool pass_inplace_supported(const uint8_t *img, size_t pitch, size_t stride, int w, int h, int ch, int nframes) {
+    return ch == 3 && w >= 3 && h >= 3 && ((uintptr_t)img & 15) == 0 && (pitch & 15) == 0 && (nframes == 1 || (stride & 15) == 0) &&
+           pitch >= (((size_t)w * 3 + 15) & ~(size_t)15);
+}
+PassScratch pass_inplace_scratch(int w, int h, int nframes, int sm_count) {
+    const TmaDecomp d = tma_decomp(w, h, nframes, 3, sm_count);
+    PassScratch s;
+    s.row_pitch = ((size_t)w * 3 + 15) & ~(size_t)15;
+    s.rows_bytes = (size_t)nframes * d.nbands * 2 * s.row_pitch;
+    s.border_bytes = (size_t)nframes * 2 * s.row_pitch;
+    s.entry_pitch = (size_t)(d.nstrips + 1) * 16;
+    s.entries_bytes = (size_t)nframes * h * s.entry_pitch;
+    return s;
+}
+template <int FMA_MODE, bool BIAS>
+static cudaError_t launch_pass_inplace_t(const StencilArgs &a, const PassSide &side, int sm_count, cudaStream_t st) {
+    return launch_sobel_tma_h<3, FMA_MODE, BIAS, 2>(a, sm_count, st, &side);
+}
+// one iteration of main_with_sobel.c:51-74 in place on `img` (3 channels): scratch = rows | border | entries as sized by pass_inplace_scratch
+cudaError_t launch_gray_sobel_pass_inplace(uint8_t *img, size_t pitch, size_t stride, int w, int h, int nframes, const uint8_t *edge, size_t epitch,
+                                           size_t estride, int fma_mode, int no_bias, uint8_t *scratch, int sm_count, cudaStream_t st) {
+    const TmaDecomp d = tma_decomp(w, h, nframes, 3, sm_count);
+    const PassScratch sz = pass_inplace_scratch(w, h, nframes, sm_count);
+    PrepParams pp{};
+    pp.img = img; pp.pitch = pitch; pp.stride = stride; pp.w = w; pp.h = h; pp.nframes = nframes;
+    pp.nbands = d.nbands; pp.rpb = d.rows_per_band; pp.nstrips = d.nstrips;
+    pp.row_bytes16 = (uint32_t)sz.row_pitch;
+    pp.edge = edge; pp.epitch = epitch; pp.estride = estride;
+    pp.rows = scratch; pp.row_pitch = sz.row_pitch;
+    pp.border = scratch + sz.rows_bytes;
+    pp.entries = scratch + sz.rows_bytes + sz.border_bytes; pp.entry_pitch = sz.entry_pitch;
+    const long long work = (long long)nframes * ((long long)(d.nbands + 1) * 2 * (sz.row_pitch / 16) + (long long)h * (d.nstrips + 1));
+    const int grid = (int)max(1LL, min((work + 255) / 256, (long long)sm_count * 16));
+    count_launch();
+    pass_prepare_kernel<<<grid, 256, 0, st>>>(pp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    StencilArgs a{};
+    a.src = img; a.dst = img; a.src_pitch = pitch; a.dst_pitch = pitch; a.src_stride = stride; a.dst_stride = stride;
+    a.width = w; a.height = h; a.channels = 3; a.nframes = nframes; a.fma_mode = fma_mode; a.no_bias = no_bias;
+    PassSide side{};
+    side.rows = pp.rows; side.row_pitch = sz.row_pitch; side.border = pp.border;
+    side.entries_base = pp.entries; side.entry_pitch = sz.entry_pitch; side.entries = d.nstrips + 1;
+    if (no_bias) return fma_mode ? launch_pass_inplace_t<1, false>(a, side, sm_count, st) : launch_pass_inplace_t<0, false>(a, side, sm_count, st);
+    return fma_mode ? launch_pass_inplace_t<1, true>(a, side, sm_count, st) : launch_pass_inplace_t<0, true>(a, side, sm_count, st);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -332,6 +332,67 @@ def test_row_bands_equal_single_pass(gpu, O):
     b.close()
 
 
+@pytest.mark.parametrize("h,w,nframes", [(1080, 1920, 2), (257, 1500, 1), (64, 2037, 3), (131, 512, 1), (3, 3, 1), (5, 17, 2), (4, 16, 1),
+                                         (262, 4112, 1), (133, 513, 1), (2160, 3840, 1), (40, 8191, 1)])
+def test_gray_sobel_pass_dev_in_place_fused(gpu, O, h, w, nframes):
+    """a5 on the device, in place (main_with_sobel.c:51-74): 3-channel images take the preparation kernel + ONE fused kernel that
+    writes RGB; two passes (the second runs on the first one's output), zero / absent / non-zero scratch border, both luma
+    modes, pitched rows whose padding must survive, widths that end inside a 16-pixel group."""
+    L = gpu.lib()
+    pitch, epitch = (w * 3 + 127) // 128 * 128, (w + 127) // 128 * 128
+    rng = np.random.default_rng(h * 10007 + w)
+    for mode, border in (("strict", None), ("strict", 0xAB), ("fma", 0)):
+        gpu.set_luma_mode(mode)
+        try:
+            frames = rng.integers(0, 256, (nframes, h, w, 3), dtype=np.uint8)
+            edge_host = None
+            if border is not None:
+                edge_host = np.zeros((nframes, h, w), np.uint8)
+                if border:
+                    edge_host[:, 0, :] = rng.integers(0, 256, (nframes, w)); edge_host[:, -1, :] = rng.integers(0, 256, (nframes, w))
+                    edge_host[:, :, 0] = rng.integers(0, 256, (nframes, h)); edge_host[:, :, -1] = rng.integers(0, 256, (nframes, h))
+                edge_host[:, 1:-1, 1:-1] = 0x5C                                # interior: must come back untouched on the fused path
+            img = to_dev_pitched(gpu, frames.reshape(nframes * h, w * 3), pitch)
+            ebuf = to_dev_pitched(gpu, edge_host.reshape(nframes * h, w), epitch) if edge_host is not None else None
+            want = [f.copy() for f in frames]
+            for p in range(2):
+                n0 = gpu.launch_count()
+                ck(gpu, L.ompimg_gray_sobel_pass_dev(img.ptr, pitch, 3, ebuf.ptr if ebuf else None, epitch, w, h, nframes, pitch * h, epitch * h, 0))
+                gpu.sync(0)
+                assert gpu.launch_count() - n0 == 2                            # preparation + the fused kernel
+                raw = from_dev_pitched(gpu, img, nframes * h, pitch, pitch)
+                for f in range(nframes):
+                    e0 = edge_host[f].copy() if edge_host is not None else None
+                    want[f], _ = O.gray_sobel_pass(want[f], e0, fma=(mode == "fma"))
+                    got = raw[f * h:(f + 1) * h, :w * 3].reshape(h, w, 3)
+                    assert np.array_equal(got, want[f]), (mode, border, p, f)
+                assert (raw[:, w * 3:] == 0xCD).all(), "row padding was written"
+            if ebuf is not None:
+                assert np.array_equal(from_dev_pitched(gpu, ebuf, nframes * h, epitch, epitch)[:, :w].reshape(nframes, h, w), edge_host)
+                ebuf.free()
+            img.free()
+        finally:
+            gpu.set_luma_mode("strict")
+
+
+def test_gray_sobel_pass_dev_other_layouts_take_two_kernels(gpu, O):
+    """4 channels (alpha must survive) and rows that are not 16-byte friendly: fused gray->Sobel into the scratch plane + replicate"""
+    L = gpu.lib()
+    rng = np.random.default_rng(5)
+    for (h, w, ch, pitch) in ((70, 333, 4, 333 * 4), (70, 333, 3, 333 * 3), (33, 640, 4, 640 * 4 + 128)):
+        img_h = rng.integers(0, 256, (h, w, ch), dtype=np.uint8)
+        edge_h = np.zeros((h, w), np.uint8); edge_h[0] = 7; edge_h[:, 0] = 9
+        img = to_dev_pitched(gpu, img_h.reshape(h, w * ch), pitch)
+        ebuf = to_dev_pitched(gpu, edge_h, w)
+        ck(gpu, L.ompimg_gray_sobel_pass_dev(img.ptr, pitch, ch, ebuf.ptr, w, w, h, 1, 0, 0, 0))
+        gpu.sync(0)
+        want_img, want_edge = O.gray_sobel_pass(img_h.copy(), edge_h.copy())
+        assert np.array_equal(from_dev_pitched(gpu, img, h, w * ch, pitch).reshape(h, w, ch), want_img)
+        assert np.array_equal(from_dev_pitched(gpu, ebuf, h, w, w), want_edge)
+        assert L.ompimg_gray_sobel_pass_dev(img.ptr, pitch, ch, None, w, w, h, 1, 0, 0, 0) == -2      # these layouts need the scratch plane
+        img.free(); ebuf.free()
+
+
 def test_row_bands_on_distinct_devices_equal_oracle(gpu, O):
     """the real peer path: every band on its own GPU, halo rows fetched by the kernel's bulk copies over NVLink
     (skips on a one-GPU box; `gpurun --gpus 2` and the 8-GPU scaling run exercise it)"""
