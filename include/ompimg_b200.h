@@ -217,6 +217,30 @@ OMPIMG_API int   ompimg_ipc_export(const void *dev_ptr, unsigned char *handle_ou
 OMPIMG_API void *ompimg_ipc_open(const unsigned char *handle);     /* NULL on failure */
 OMPIMG_API int   ompimg_ipc_close(void *mapped);
 
+/* ---- JPEG decode in front of the kernels ---------------------------------------------------------
+ * monolithic/src/main.c:21 decodes its input with the vendored stb_image v2.30 (stbi_load, req_comp 0) on one CPU core; on
+ * `test.jpg` that takes longer than every kernel pass together.  Here the serial part (markers, Huffman, progressive passes)
+ * runs on the host and yields quantised coefficients; dequantisation, IDCT, chroma upsampling and YCbCr->RGB run on the
+ * GPU in stb_image's own integer arithmetic (stb_image.h:2430-2524, 3464-3527, 3659-3683), so the pixels equal the
+ * reference's byte for byte.  Handles what stb's JPEG path handles for 8-bit Huffman files with 1 or 3 components and
+ * sampling factors 1 and 2 (baseline and progressive, restart intervals); anything else is refused with OMPIMG_ERR_ARG.
+ * Output: interleaved RGB (3 components) or the single plane, like stbi_load(..., 0). */
+typedef struct ompimg_jpeg ompimg_jpeg;
+OMPIMG_API int          ompimg_jpeg_probe(const uint8_t *bytes, size_t nbytes, int *width, int *height, int *channels);   /* header only */
+OMPIMG_API ompimg_jpeg *ompimg_jpeg_parse(const uint8_t *bytes, size_t nbytes);      /* host only (no CUDA): entropy decoding; NULL on error */
+OMPIMG_API void         ompimg_jpeg_free(ompimg_jpeg *j);
+OMPIMG_API int          ompimg_jpeg_info(const ompimg_jpeg *j, int *width, int *height, int *channels);
+OMPIMG_API int          ompimg_jpeg_to_rgb_dev(const ompimg_jpeg *j, uint8_t *out_dev, size_t pitch, int stream);     /* synchronises the stream */
+OMPIMG_API int          ompimg_jpeg_to_rgb_host(const ompimg_jpeg *j, uint8_t *out_host);    /* dense width*height*channels */
+/* main.c:21-35 as one call: decode, `passes` x convert_to_grayscale on the device, one download of width*height*channels bytes */
+OMPIMG_API int          ompimg_jpeg_gray_host(const uint8_t *bytes, size_t nbytes, int passes, uint8_t *out_host, size_t out_capacity,
+                                              int *width, int *height, int *channels);
+/* for tests: component c's sampling factors, block grid, effective samples, coefficients [blocks_h][blocks_w][64] (natural
+ * order, not dequantised) and its quantisation table; whether the three components are YCbCr (1) or already RGB (0) */
+OMPIMG_API int          ompimg_jpeg_component(const ompimg_jpeg *j, int c, int *h_samp, int *v_samp, int *blocks_w, int *blocks_h,
+                                              int *samples_x, int *samples_y, const int16_t **coeff, const uint16_t **dequant);
+OMPIMG_API int          ompimg_jpeg_color_transform(const ompimg_jpeg *j);
+
 /* ---- persistent worker mode (the reference's services exec the CLI once per request,
  * microservices/grayscale/app.py:24-34, event-driven/grayscale_service/app.py:54-65) -----------------
  * With OMPIMG_WORKER=<unix socket path> in the environment the two frozen prototypes do not create a

@@ -114,6 +114,15 @@ _SIGS = {
     "ompimg_bands_rgb_to_edge": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "ompimg_bands_download_edge": (C.c_int, [_vp, _vp]),
     "ompimg_bands_checksum": (C.c_int, [_vp, C.POINTER(C.c_ulonglong)]),
+    "ompimg_jpeg_probe": (C.c_int, [_vp, _sz, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ompimg_jpeg_parse": (_vp, [_vp, _sz]),
+    "ompimg_jpeg_free": (None, [_vp]),
+    "ompimg_jpeg_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ompimg_jpeg_to_rgb_dev": (C.c_int, [_vp, _vp, _sz, C.c_int]),
+    "ompimg_jpeg_to_rgb_host": (C.c_int, [_vp, _vp]),
+    "ompimg_jpeg_gray_host": (C.c_int, [_vp, _sz, C.c_int, _vp, _sz, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ompimg_jpeg_component": (C.c_int, [_vp, C.c_int] + [C.POINTER(C.c_int)] * 6 + [C.POINTER(_vp), C.POINTER(_vp)]),
+    "ompimg_jpeg_color_transform": (C.c_int, [_vp]),
     "ompimg_ipc_export": (C.c_int, [_vp, _vp]),
     "ompimg_ipc_open": (_vp, [_vp]),
     "ompimg_ipc_close": (C.c_int, [_vp]),
@@ -371,6 +380,64 @@ def isqrt_table(count: int, bias: float = 0.5) -> np.ndarray:
 
 def synth_dev(buf: DeviceBuffer, nbytes: int, seed: int, offset: int = 0, dst_offset: int = 0, stream: int = 0):
     _ck(lib().ompimg_synth_fill_dev(buf.ptr + dst_offset, nbytes, seed & 0xFFFFFFFF, offset, stream), "synth_fill")
+
+
+# ------------------------------------------------------------------------------------------------
+# JPEG decode in front of the kernels (monolithic/src/main.c:21: stbi_load)
+# ------------------------------------------------------------------------------------------------
+class Jpeg:
+    """A parsed JPEG: entropy decoding done on the host (works without a GPU), pixels produced on the device."""
+
+    def __init__(self, data: bytes):
+        self._buf = np.frombuffer(data, np.uint8)
+        self.h_ = lib().ompimg_jpeg_parse(_ptr(self._buf), self._buf.size)
+        if not self.h_:
+            raise OmpimgError("ompimg_jpeg_parse: " + lib().ompimg_last_error().decode())
+        w, h, ch = C.c_int(), C.c_int(), C.c_int()
+        _ck(lib().ompimg_jpeg_info(self.h_, C.byref(w), C.byref(h), C.byref(ch)), "jpeg_info")
+        self.width, self.height, self.channels = w.value, h.value, ch.value
+
+    def component(self, c: int) -> dict:
+        """sampling factors, block grid, coefficient blocks (copy) and quantisation table of component c (tests)"""
+        v = [C.c_int() for _ in range(6)]
+        pc, pq = _vp(), _vp()
+        _ck(lib().ompimg_jpeg_component(self.h_, c, *[C.byref(x) for x in v], C.byref(pc), C.byref(pq)), "jpeg_component")
+        hs, vs, bw, bh, sx, sy = [x.value for x in v]
+        coeff = np.ctypeslib.as_array((C.c_int16 * (bw * bh * 64)).from_address(pc.value)).reshape(bh, bw, 64).copy()
+        dq = np.ctypeslib.as_array((C.c_uint16 * 64).from_address(pq.value)).copy()
+        return {"h": hs, "v": vs, "bw": bw, "bh": bh, "x": sx, "y": sy, "coeff": coeff, "dequant": dq}
+
+    @property
+    def ycbcr(self) -> bool:
+        return lib().ompimg_jpeg_color_transform(self.h_) == 1
+
+    def decode(self) -> np.ndarray:
+        """H x W x 3 (or H x W) uint8, equal to stbi_load(path, ..., 0)"""
+        shape = (self.height, self.width, 3) if self.channels == 3 else (self.height, self.width)
+        out = np.empty(shape, np.uint8)
+        _ck(lib().ompimg_jpeg_to_rgb_host(self.h_, _ptr(out)), "jpeg_to_rgb_host")
+        return out
+
+    def close(self):
+        if self.h_:
+            lib().ompimg_jpeg_free(self.h_)
+            self.h_ = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def jpeg_gray(data: bytes, passes: int = 1) -> np.ndarray:
+    """main.c:21-35: decode + `passes` x convert_to_grayscale, one device round trip"""
+    buf = np.frombuffer(data, np.uint8)
+    w, h, ch = C.c_int(), C.c_int(), C.c_int()
+    _ck(lib().ompimg_jpeg_probe(_ptr(buf), buf.size, C.byref(w), C.byref(h), C.byref(ch)), "jpeg_probe")
+    out = np.empty((h.value, w.value, ch.value) if ch.value == 3 else (h.value, w.value), np.uint8)
+    _ck(lib().ompimg_jpeg_gray_host(_ptr(buf), buf.size, passes, _ptr(out), out.nbytes, C.byref(w), C.byref(h), C.byref(ch)), "jpeg_gray_host")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

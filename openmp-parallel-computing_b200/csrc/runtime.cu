@@ -10,10 +10,13 @@
 #include <condition_variable>
 #include <functional>
 #include <mutex>
+#include <new>
+#include <string>
 #include <thread>
 #include <vector>
 
 #include "../../include/ompimg_b200.h"
+#include "jpeg.h"
 #include "kernels.h"
 #include "worker.h"
 
@@ -987,6 +990,108 @@ extern "C" int ompimg_gray_avg3_host(const uint8_t *rgb, uint8_t *out, int rows,
     CK(cudaMemcpyAsync(min_max, dmm, 8, cudaMemcpyDeviceToHost, g.streams[0]));
     CK(cudaStreamSynchronize(g.streams[0]));
     return OMPIMG_OK;
+}
+
+// =================================================================================================
+// JPEG decode in front of the kernels (monolithic/src/main.c:21)
+// =================================================================================================
+struct ompimg_jpeg { JpegCoeffs jc; };
+
+extern "C" ompimg_jpeg *ompimg_jpeg_parse(const uint8_t *bytes, size_t nbytes) {
+    if (!bytes) { fail(OMPIMG_ERR_ARG, "invalid argument: bytes"); return nullptr; }
+    ompimg_jpeg *j = new (std::nothrow) ompimg_jpeg();
+    if (!j) { fail(OMPIMG_ERR_NOMEM, "out of host memory"); return nullptr; }
+    std::string err;
+    if (!jpeg_entropy_decode(bytes, nbytes, j->jc, err)) {
+        fail(OMPIMG_ERR_ARG, "JPEG: %s", err.c_str());
+        delete j;
+        return nullptr;
+    }
+    return j;
+}
+extern "C" void ompimg_jpeg_free(ompimg_jpeg *j) { delete j; }
+extern "C" int ompimg_jpeg_info(const ompimg_jpeg *j, int *w, int *h, int *channels) {
+    NEED(j, "jpeg");
+    if (w) *w = j->jc.width;
+    if (h) *h = j->jc.height;
+    if (channels) *channels = j->jc.out_channels();
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_jpeg_probe(const uint8_t *bytes, size_t nbytes, int *w, int *h, int *channels) {
+    NEED(bytes, "bytes");
+    return jpeg_probe(bytes, nbytes, w, h, channels) ? OMPIMG_OK : fail(OMPIMG_ERR_ARG, "not a JPEG this decoder handles (8-bit, 1 or 3 components, Huffman)");
+}
+extern "C" int ompimg_jpeg_component(const ompimg_jpeg *j, int c, int *h_samp, int *v_samp, int *blocks_w, int *blocks_h, int *samples_x, int *samples_y,
+                                     const int16_t **coeff, const uint16_t **dequant) {
+    NEED(j && c >= 0 && c < j->jc.ncomp, "component");
+    const JpegComp &k = j->jc.comp[c];
+    if (h_samp) *h_samp = k.h;
+    if (v_samp) *v_samp = k.v;
+    if (blocks_w) *blocks_w = k.bw;
+    if (blocks_h) *blocks_h = k.bh;
+    if (samples_x) *samples_x = k.x;
+    if (samples_y) *samples_y = k.y;
+    if (coeff) *coeff = k.coeff.data();
+    if (dequant) *dequant = j->jc.dequant[k.tq];
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_jpeg_color_transform(const ompimg_jpeg *j) {
+    if (!j) return -1;
+    return j->jc.ncomp == 3 && !(j->jc.ids_are_rgb || (j->jc.app14_transform == 0 && !j->jc.jfif)) ? 1 : 0;
+}
+static int jpeg_to_dev(const ompimg_jpeg *j, uint8_t *out_dev, size_t pitch, cudaStream_t st) {
+    RESERVE(g.scratch[4], jpeg_device_scratch_bytes(j->jc) + 256);
+    CK(launch_jpeg_backend(j->jc, (uint8_t *)g.scratch[4].p, out_dev, pitch, g.sm_count, st));
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_jpeg_to_rgb_dev(const ompimg_jpeg *j, uint8_t *out_dev, size_t pitch, int stream) {
+    INIT(); STREAM(stream, st);
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    NEED(j && out_dev, "jpeg");
+    NEED(pitch >= (size_t)j->jc.width * j->jc.out_channels(), "pitch");
+    int rc = jpeg_to_dev(j, out_dev, pitch, st);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(st));               // the coefficients are read from the handle's host memory: done before the caller may free it
+    return OMPIMG_OK;
+}
+extern "C" int ompimg_jpeg_to_rgb_host(const ompimg_jpeg *j, uint8_t *out_host) {
+    INIT();
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    NEED(j && out_host, "jpeg");
+    const size_t row = (size_t)j->jc.width * j->jc.out_channels(), bytes = row * j->jc.height;
+    RESERVE(g.scratch[0], bytes + 256);
+    cudaStream_t st = g.streams[0];
+    int rc = jpeg_to_dev(j, (uint8_t *)g.scratch[0].p, row, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_host, g.scratch[0].p, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return OMPIMG_OK;
+}
+// main.c:21-35 in one call: decode, then `passes` x convert_to_grayscale on the device, one download.  1-channel JPEGs come back
+// as decoded (channels 1 is undefined behaviour in the reference's kernel: the image is left alone, see convert_to_grayscale).
+extern "C" int ompimg_jpeg_gray_host(const uint8_t *bytes, size_t nbytes, int passes, uint8_t *out_host, size_t out_capacity, int *w, int *h, int *channels) {
+    INIT();
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    NEED(bytes && out_host, "buffers");
+    ompimg_jpeg *j = ompimg_jpeg_parse(bytes, nbytes);
+    if (!j) return OMPIMG_ERR_ARG;
+    const int ch = j->jc.out_channels(), W = j->jc.width, H = j->jc.height;
+    const size_t row = (size_t)W * ch, total = row * H;
+    if (w) *w = W;
+    if (h) *h = H;
+    if (channels) *channels = ch;
+    int rc = OMPIMG_OK;
+    if (total > out_capacity) rc = fail(OMPIMG_ERR_ARG, "output buffer too small: %zu bytes needed", total);
+    cudaStream_t st = g.streams[0];
+    if (!rc) rc = reserve(g.scratch[0], total + 256);
+    if (!rc) rc = jpeg_to_dev(j, (uint8_t *)g.scratch[0].p, row, st);
+    if (!rc && ch == 3)
+        for (int p = 0; p < (passes < 1 ? 1 : passes) && !rc; ++p)
+            if (launch_gray_inplace((uint8_t *)g.scratch[0].p, row, W, H, 3, 1, 0, g.luma_mode, g.sm_count, st) != cudaSuccess) rc = fail(OMPIMG_ERR_CUDA, "grayscale launch failed");
+    if (!rc && cudaMemcpyAsync(out_host, g.scratch[0].p, total, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = fail(OMPIMG_ERR_CUDA, "download failed");
+    if (cudaStreamSynchronize(st) != cudaSuccess && !rc) rc = fail(OMPIMG_ERR_CUDA, "stream synchronisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ompimg_jpeg_free(j);
+    return rc;
 }
 
 // =================================================================================================

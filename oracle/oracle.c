@@ -335,3 +335,99 @@ ORACLE_API void *oracle_table3_alloc(long *base, int rows, int cols)
     return top;
 }
 ORACLE_API void oracle_table3_free(void *t) { free(t); }
+
+/* --- f2: the JPEG back end (stb_image v2.30 as vendored by the reference, monolithic/include/stb_image.h) -----------
+ * TEST INFRASTRUCTURE: a scalar restatement of what stb does AFTER entropy decoding, used (a) on the CPU to check the
+ * product's host-side entropy decoder without a GPU and (b) as a second statement of the arithmetic next to the real
+ * checker, the reference's own stb_image.h compiled as it lies (oracle/tools/stb_decode.c -> oracle/_ref/bin/stb_decode).
+ *   dequantise  stb_image.h:2227,2245,3073-3078 (short arithmetic)     IDCT      stb_image.h:2430-2524
+ *   resampling  stb_image.h:3464-3527, row pairing :3907-3941           colour    stb_image.h:3659-3683
+ * comp[k]: coeff [bh][bw][64] natural order, dq[64]; planes are produced internally.  out: w*h*(ncomp==3?3:1) bytes. */
+#define OJ_F2F(x) ((int)(((x) * 4096 + 0.5)))
+#define OJ_IDCT_1D(s0,s1,s2,s3,s4,s5,s6,s7) \
+   int t0,t1,t2,t3,p1,p2,p3,p4,p5,x0,x1,x2,x3; \
+   p2 = s2; p3 = s6; p1 = (p2+p3) * OJ_F2F(0.5411961f); t2 = p1 + p3*OJ_F2F(-1.847759065f); t3 = p1 + p2*OJ_F2F(0.765366865f); \
+   p2 = s0; p3 = s4; t0 = (p2+p3)*4096; t1 = (p2-p3)*4096; x0 = t0+t3; x3 = t0-t3; x1 = t1+t2; x2 = t1-t2; \
+   t0 = s7; t1 = s5; t2 = s3; t3 = s1; p3 = t0+t2; p4 = t1+t3; p1 = t0+t3; p2 = t1+t2; p5 = (p3+p4)*OJ_F2F(1.175875602f); \
+   t0 = t0*OJ_F2F(0.298631336f); t1 = t1*OJ_F2F(2.053119869f); t2 = t2*OJ_F2F(3.072711026f); t3 = t3*OJ_F2F(1.501321110f); \
+   p1 = p5 + p1*OJ_F2F(-0.899976223f); p2 = p5 + p2*OJ_F2F(-2.562915447f); p3 = p3*OJ_F2F(-1.961570560f); p4 = p4*OJ_F2F(-0.390180644f); \
+   t3 += p1+p4; t2 += p2+p3; t1 += p2+p4; t0 += p1+p3;
+static unsigned char oj_clamp(int x) { return (unsigned char)(x < 0 ? 0 : x > 255 ? 255 : x); }
+static void oj_idct(unsigned char *out, int stride, const short *in, const unsigned short *dq)
+{
+    short d[64];
+    int v[64];
+    for (int i = 0; i < 64; ++i) d[i] = (short)(in[i] * dq[i]);
+    for (int i = 0; i < 8; ++i) {
+        OJ_IDCT_1D(d[i], d[8+i], d[16+i], d[24+i], d[32+i], d[40+i], d[48+i], d[56+i])
+        x0 += 512; x1 += 512; x2 += 512; x3 += 512;
+        v[i] = (x0+t3) >> 10; v[56+i] = (x0-t3) >> 10; v[8+i] = (x1+t2) >> 10; v[48+i] = (x1-t2) >> 10;
+        v[16+i] = (x2+t1) >> 10; v[40+i] = (x2-t1) >> 10; v[24+i] = (x3+t0) >> 10; v[32+i] = (x3-t0) >> 10;
+    }
+    for (int i = 0; i < 8; ++i) {
+        unsigned char *o = out + (size_t)i * stride;
+        OJ_IDCT_1D(v[8*i], v[8*i+1], v[8*i+2], v[8*i+3], v[8*i+4], v[8*i+5], v[8*i+6], v[8*i+7])
+        x0 += 65536 + (128<<17); x1 += 65536 + (128<<17); x2 += 65536 + (128<<17); x3 += 65536 + (128<<17);
+        o[0] = oj_clamp((x0+t3) >> 17); o[7] = oj_clamp((x0-t3) >> 17); o[1] = oj_clamp((x1+t2) >> 17); o[6] = oj_clamp((x1-t2) >> 17);
+        o[2] = oj_clamp((x2+t1) >> 17); o[5] = oj_clamp((x2-t1) >> 17); o[3] = oj_clamp((x3+t0) >> 17); o[4] = oj_clamp((x3-t0) >> 17);
+    }
+}
+/* one output row of component k, resampled to full width like stb's row functions; returns the row to read from */
+static const unsigned char *oj_resample(unsigned char *buf, const unsigned char *near, const unsigned char *far, int w, int hs, int vs)
+{
+    if (hs == 1 && vs == 1) return near;
+    if (hs == 1) { for (int i = 0; i < w; ++i) buf[i] = (unsigned char)((3*near[i] + far[i] + 2) >> 2); return buf; }
+    if (vs == 1) {
+        if (w == 1) { buf[0] = buf[1] = near[0]; return buf; }
+        buf[0] = near[0]; buf[1] = (unsigned char)((near[0]*3 + near[1] + 2) >> 2);
+        int i;
+        for (i = 1; i < w-1; ++i) { int n = 3*near[i]+2; buf[i*2] = (unsigned char)((n+near[i-1]) >> 2); buf[i*2+1] = (unsigned char)((n+near[i+1]) >> 2); }
+        buf[i*2] = (unsigned char)((near[w-2]*3 + near[w-1] + 2) >> 2); buf[i*2+1] = near[w-1];
+        return buf;
+    }
+    if (w == 1) { buf[0] = buf[1] = (unsigned char)((3*near[0] + far[0] + 2) >> 2); return buf; }
+    int t0, t1 = 3*near[0] + far[0];
+    buf[0] = (unsigned char)((t1+2) >> 2);
+    for (int i = 1; i < w; ++i) { t0 = t1; t1 = 3*near[i]+far[i]; buf[i*2-1] = (unsigned char)((3*t0 + t1 + 8) >> 4); buf[i*2] = (unsigned char)((3*t1 + t0 + 8) >> 4); }
+    buf[w*2-1] = (unsigned char)((t1+2) >> 2);
+    return buf;
+}
+#define OJ_FIX(x) (((int)((x) * 4096.0f + 0.5f)) << 8)
+ORACLE_API int oracle_jpeg_backend(int width, int height, int ncomp, int hmax, int vmax, int ycbcr,
+                                   const short *const *coeff, const unsigned short *const *dq, const int *ch, const int *cv,
+                                   const int *bw, const int *bh, const int *cy, unsigned char *out)
+{
+    unsigned char *plane[3] = {0, 0, 0}, *line[3] = {0, 0, 0};
+    if (ncomp != 1 && ncomp != 3) return -1;
+    for (int k = 0; k < ncomp; ++k) {
+        plane[k] = (unsigned char *)malloc((size_t)bw[k] * bh[k] * 64);
+        line[k] = (unsigned char *)malloc((size_t)width + 8);
+        for (int by = 0; by < bh[k]; ++by)
+            for (int bx = 0; bx < bw[k]; ++bx)
+                oj_idct(plane[k] + ((size_t)by * 8) * bw[k] * 8 + bx * 8, bw[k] * 8, coeff[k] + ((size_t)by * bw[k] + bx) * 64, dq[k]);
+    }
+    const int n = ncomp == 3 ? 3 : 1;
+    int ystep[3], ypos[3];
+    const unsigned char *l0[3], *l1[3];
+    for (int k = 0; k < ncomp; ++k) { ystep[k] = (vmax / cv[k]) >> 1; ypos[k] = 0; l0[k] = l1[k] = plane[k]; }
+    for (int j = 0; j < height; ++j) {
+        const unsigned char *row[3];
+        for (int k = 0; k < ncomp; ++k) {
+            const int hs = hmax / ch[k], vs = vmax / cv[k], y_bot = ystep[k] >= (vs >> 1);
+            row[k] = oj_resample(line[k], y_bot ? l1[k] : l0[k], y_bot ? l0[k] : l1[k], (width + hs - 1) / hs, hs, vs);
+            if (++ystep[k] >= vs) { ystep[k] = 0; l0[k] = l1[k]; if (++ypos[k] < cy[k]) l1[k] += bw[k] * 8; }
+        }
+        unsigned char *o = out + (size_t)j * width * n;
+        for (int i = 0; i < width; ++i, o += n) {
+            if (ncomp == 1) { o[0] = row[0][i]; continue; }
+            if (!ycbcr) { o[0] = row[0][i]; o[1] = row[1][i]; o[2] = row[2][i]; continue; }
+            int y_fixed = (row[0][i] << 20) + (1<<19), cr = row[2][i] - 128, cb = row[1][i] - 128;
+            int r = y_fixed + cr * OJ_FIX(1.40200f);
+            int g = y_fixed + (cr * -OJ_FIX(0.71414f)) + ((cb * -OJ_FIX(0.34414f)) & 0xffff0000);
+            int b = y_fixed + cb * OJ_FIX(1.77200f);
+            o[0] = oj_clamp(r >> 20); o[1] = oj_clamp(g >> 20); o[2] = oj_clamp(b >> 20);
+        }
+    }
+    for (int k = 0; k < ncomp; ++k) { free(plane[k]); free(line[k]); }
+    return 0;
+}

@@ -314,6 +314,41 @@ class RefOld:
         return out, mm
 
 
+def jpeg_backend(width: int, height: int, comps: list, ycbcr: bool) -> np.ndarray:
+    """stb_image's JPEG back end (dequantise, IDCT, resample, colour) restated, from per-component coefficient blocks:
+    comps[k] = {"h", "v", "bw", "bh", "y", "coeff" int16 [bh][bw][64], "dequant" uint16 [64]} (monolithic/include/stb_image.h)."""
+    n = len(comps)
+    L = lib()
+    L.oracle_jpeg_backend.restype = C.c_int
+    hmax, vmax = max(c["h"] for c in comps), max(c["v"] for c in comps)
+    coeff = [np.ascontiguousarray(c["coeff"], np.int16) for c in comps]
+    dq = [np.ascontiguousarray(c["dequant"], np.uint16) for c in comps]
+    PP = C.c_void_p * n
+    IA = C.c_int * n
+    out = np.empty((height, width, 3) if n == 3 else (height, width), np.uint8)
+    rc = L.oracle_jpeg_backend(C.c_int(width), C.c_int(height), C.c_int(n), C.c_int(hmax), C.c_int(vmax), C.c_int(int(ycbcr)),
+                               PP(*[a.ctypes.data for a in coeff]), PP(*[a.ctypes.data for a in dq]),
+                               IA(*[c["h"] for c in comps]), IA(*[c["v"] for c in comps]), IA(*[c["bw"] for c in comps]), IA(*[c["bh"] for c in comps]),
+                               IA(*[c["y"] for c in comps]), out.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return out
+
+
+def stb_decode(path) -> np.ndarray | None:
+    """the reference's own stb_image.h (oracle/_ref/bin/stb_decode, built by `make -C oracle ref`): stbi_load(path, ..., 0)"""
+    exe = REF_DIR / "bin" / "stb_decode"
+    if not exe.exists():
+        return None
+    import tempfile
+    with tempfile.NamedTemporaryFile(suffix=".raw") as t:
+        r = subprocess.run([str(exe), str(path), t.name], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("stb_decode failed: " + r.stderr)
+        w, h, ch = map(int, r.stdout.split())
+        a = np.fromfile(t.name, np.uint8)
+    return a.reshape(h, w, ch) if ch > 1 else a.reshape(h, w)
+
+
 def omp_max_threads() -> int:
     return int(lib().oracle_omp_max_threads())
 
