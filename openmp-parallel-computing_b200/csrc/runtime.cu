@@ -1070,6 +1070,18 @@ extern "C" int ompimg_jpeg_to_rgb_host(const ompimg_jpeg *j, uint8_t *out_host) 
 // main.c:21-35 in one call: decode, then `passes` x convert_to_grayscale on the device, one download.  1-channel JPEGs come back
 // as decoded (channels 1 is undefined behaviour in the reference's kernel: the image is left alone, see convert_to_grayscale).
 extern "C" int ompimg_jpeg_gray_host(const uint8_t *bytes, size_t nbytes, int passes, uint8_t *out_host, size_t out_capacity, int *w, int *h, int *channels) {
+    if (!g.ready && bytes && out_host && getenv("OMPIMG_WORKER")) {
+        // persistent worker mode: this process creates no CUDA context; the FILE travels (a tenth of the pixels), the pixels come back
+        int pw = 0, ph = 0, pc = 0;
+        if (!jpeg_probe(bytes, nbytes, &pw, &ph, &pc)) return fail(OMPIMG_ERR_ARG, "not a JPEG this decoder handles (8-bit, 1 or 3 components, Huffman)");
+        const size_t total = (size_t)pw * ph * pc;
+        if (total > out_capacity) return fail(OMPIMG_ERR_ARG, "output buffer too small: %zu bytes needed", total);
+        const char *m = getenv("OMPIMG_LUMA");
+        const int mode = (m && (!strcmp(m, "fma") || !strcmp(m, "1"))) ? OMPIMG_LUMA_FMA : OMPIMG_LUMA_STRICT;
+        const int rc = worker_call_jpeg_gray(bytes, nbytes, passes, mode, out_host, total, pw, ph, pc, g_err, sizeof g_err);
+        if (rc == 1) { if (w) *w = pw; if (h) *h = ph; if (channels) *channels = pc; return OMPIMG_OK; }
+        if (rc < 0) return rc;
+    }
     INIT();
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     NEED(bytes && out_host, "buffers");

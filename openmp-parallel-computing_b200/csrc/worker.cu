@@ -43,7 +43,7 @@ namespace ompimg {
 namespace {
 
 constexpr uint32_t WK_MAGIC = 0x4F4D5042u;      // "OMPB"
-enum : uint32_t { WK_GRAY = 1, WK_SOBEL = 2, WK_PING = 3 };
+enum : uint32_t { WK_GRAY = 1, WK_SOBEL = 2, WK_PING = 3, WK_JPEG_GRAY = 4 };   // 4: payload = a JPEG file, reply = decoded + grayscaled pixels; `reserved` = passes
 
 enum : uint32_t { WK_SHM = 1, WK_NEWFD = 2 };     // flags: payload in the shared mapping / its descriptor rides on this message
 struct WkRequest {
@@ -155,7 +155,7 @@ int client_connect(const char *path) {
 
 // 1: served by the worker (result in `out`), 0: no worker configured or reachable, < 0: the worker answered with an error
 int worker_call(uint32_t op, int w, int h, int ch, int luma_mode, const void *in, size_t in_bytes, void *out, size_t out_bytes,
-                char *err, size_t err_cap) {
+                char *err, size_t err_cap, uint32_t reserved = 0) {
     const char *path = getenv("OMPIMG_WORKER");
     if (!path || !*path) return 0;
     std::lock_guard<std::mutex> lk(g_client_mu);
@@ -171,7 +171,7 @@ int worker_call(uint32_t op, int w, int h, int ch, int luma_mode, const void *in
     const bool in_place = in == out;
     const uint64_t out_off = in_place ? 0 : shm_out_offset(in_bytes);
     const bool shm = shm_reserve((size_t)out_off + out_bytes);
-    WkRequest rq{WK_MAGIC, op, w, h, ch, luma_mode, 0u, 0u, (uint64_t)in_bytes};
+    WkRequest rq{WK_MAGIC, op, w, h, ch, luma_mode, 0u, reserved, (uint64_t)in_bytes};
     WkReply rp{};
     bool ok;
     if (shm) {
@@ -203,6 +203,12 @@ int worker_call(uint32_t op, int w, int h, int ch, int luma_mode, const void *in
 int worker_call_gray(unsigned char *data, int w, int h, int ch, int luma_mode, char *err, size_t err_cap) {
     const size_t n = (size_t)w * h * ch;
     return worker_call(WK_GRAY, w, h, ch, luma_mode, data, n, data, n, err, err_cap);
+}
+
+// main.c:21-35 through the worker: the JPEG file goes over (a tenth of the pixels' size), the grayscaled pixels come back
+int worker_call_jpeg_gray(const unsigned char *jpeg, size_t nbytes, int passes, int luma_mode, unsigned char *out, size_t out_bytes, int w, int h, int ch,
+                          char *err, size_t err_cap) {
+    return worker_call(WK_JPEG_GRAY, w, h, ch, luma_mode, jpeg, nbytes, out, out_bytes, err, err_cap, (uint32_t)(passes < 1 ? 1 : passes));
 }
 
 // the reference never writes dst's border (sobel.c:11-12): the plane comes back whole, only its interior is copied
@@ -316,26 +322,30 @@ void serve_connection(int fd) {
         }
         if (rq.magic != WK_MAGIC) break;
         const long long px = (long long)rq.width * rq.height;
-        const uint64_t want = rq.op == WK_GRAY ? (uint64_t)px * (uint64_t)rq.channels : rq.op == WK_SOBEL ? (uint64_t)px : 0;
+        const bool jpeg = rq.op == WK_JPEG_GRAY;
+        const uint64_t want = rq.op == WK_GRAY ? (uint64_t)px * (uint64_t)rq.channels : rq.op == WK_SOBEL ? (uint64_t)px : jpeg ? rq.nbytes : 0;
         if (rq.op == WK_PING) { WkReply rp{}; rp.magic = WK_MAGIC; if (!write_full(fd, &rp, sizeof rp)) break; continue; }
-        if (rq.width <= 0 || rq.height <= 0 || rq.nbytes != want || (rq.op != WK_GRAY && rq.op != WK_SOBEL) || rq.nbytes > max_request_bytes()) {
+        if (rq.width <= 0 || rq.height <= 0 || rq.nbytes != want || rq.nbytes == 0 || (rq.op != WK_GRAY && rq.op != WK_SOBEL && !jpeg) ||
+            rq.nbytes > max_request_bytes() || (jpeg && ((rq.channels != 1 && rq.channels != 3) || (uint64_t)px * (uint64_t)rq.channels > max_request_bytes()))) {
             reply_error(fd, OMPIMG_ERR_ARG, "malformed request");
             break;
         }
+        const uint64_t out_bytes = jpeg ? (uint64_t)px * (uint64_t)rq.channels : rq.nbytes;      // the client announces the decoded size it expects
+        const bool separate_out = rq.op == WK_SOBEL || jpeg;
         const bool shm = (rq.flags & WK_SHM) != 0;
         uint8_t *src, *dst;
         if (shm) {
-            const uint64_t out_off = rq.op == WK_SOBEL ? shm_out_offset(rq.nbytes) : 0;
-            if (!map || out_off + rq.nbytes > map_len) { reply_error(fd, OMPIMG_ERR_ARG, "shared mapping missing or too small"); break; }
+            const uint64_t out_off = separate_out ? shm_out_offset(rq.nbytes) : 0;
+            if (!map || out_off + out_bytes > map_len) { reply_error(fd, OMPIMG_ERR_ARG, "shared mapping missing or too small"); break; }
             src = map; dst = map + out_off;
         } else {
-            if (!in.reserve(rq.nbytes) || (rq.op == WK_SOBEL && !out.reserve(rq.nbytes))) {
+            if (!in.reserve(rq.nbytes) || (separate_out && !out.reserve(out_bytes))) {
                 reply_error(fd, OMPIMG_ERR_NOMEM, "pinned allocation failed");
                 break;
             }
             if (!read_full(fd, in.p, rq.nbytes)) break;
             src = static_cast<uint8_t *>(in.p);
-            dst = rq.op == WK_SOBEL ? static_cast<uint8_t *>(out.p) : src;
+            dst = separate_out ? static_cast<uint8_t *>(out.p) : src;
             if (rq.op == WK_SOBEL) {
                 // sobel_edge never writes the border and the pooled plane held an earlier client's result: zero the border
                 const size_t w = (size_t)rq.width, h = (size_t)rq.height;
@@ -350,14 +360,19 @@ void serve_connection(int fd) {
             if (rq.op == WK_GRAY) {
                 rc = ompimg_set_luma_mode(rq.luma_mode);
                 if (rc == OMPIMG_OK) rc = ompimg_gray_inplace_host(src, rq.width, rq.height, rq.channels);
+            } else if (jpeg) {
+                int w = 0, h = 0, ch = 0;
+                rc = ompimg_set_luma_mode(rq.luma_mode);
+                if (rc == OMPIMG_OK) rc = ompimg_jpeg_gray_host(src, rq.nbytes, (int)rq.reserved, dst, out_bytes, &w, &h, &ch);
+                if (rc == OMPIMG_OK && (w != rq.width || h != rq.height || ch != rq.channels)) { reply_error(fd, OMPIMG_ERR_ARG, "the JPEG is not the size the request announced"); continue; }
             } else {
                 rc = (rq.width < 3 || rq.height < 3) ? OMPIMG_OK : ompimg_sobel_host(src, dst, rq.width, rq.height);
             }
             if (rc != OMPIMG_OK) { reply_error(fd, rc, ompimg_last_error()); continue; }
         }
         WkReply rp{};
-        rp.magic = WK_MAGIC; rp.status = OMPIMG_OK; rp.nbytes = rq.nbytes;
-        if (!write_full(fd, &rp, sizeof rp) || (!shm && !write_full(fd, dst, rq.nbytes))) break;
+        rp.magic = WK_MAGIC; rp.status = OMPIMG_OK; rp.nbytes = out_bytes;
+        if (!write_full(fd, &rp, sizeof rp) || (!shm && !write_full(fd, dst, out_bytes))) break;
     }
     if (map) munmap(map, map_len);
     pool_give(in);

@@ -7,4 +7,6 @@ namespace ompimg {
 // < 0: the worker answered with an error (message in err)
 int worker_call_gray(unsigned char *data, int w, int h, int ch, int luma_mode, char *err, size_t err_cap);
 int worker_call_sobel(const unsigned char *src, unsigned char *dst, int w, int h, char *err, size_t err_cap);
+int worker_call_jpeg_gray(const unsigned char *jpeg, size_t nbytes, int passes, int luma_mode, unsigned char *out, size_t out_bytes, int w, int h, int ch,
+                          char *err, size_t err_cap);
 }  // namespace ompimg

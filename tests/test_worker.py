@@ -86,7 +86,7 @@ class FakeWorker:
                     shm = mmap.mmap(fds[0], 0)
                     for f in fds:
                         os.close(f)
-                magic, op, w, h, ch, mode, flags, _, n = REQ.unpack(hdr)
+                magic, op, w, h, ch, mode, flags, reserved, n = REQ.unpack(hdr)   # reserved = passes for op 4
                 assert magic == MAGIC
                 assert bool(flags & WK_NEWFD) == bool(fds)
                 if flags & WK_SHM:
@@ -100,6 +100,22 @@ class FakeWorker:
                 if op == 1:
                     img = np.frombuffer(data, np.uint8).reshape(h, w, ch).copy()
                     out, off = self.O.gray_inplace(img, ch, fma=bool(mode)), 0
+                elif op == 4:                                       # a JPEG file in, decoded + grayscaled pixels out (`reserved` = passes)
+                    import tempfile
+                    with tempfile.NamedTemporaryFile(suffix=".jpg") as t:
+                        t.write(data); t.flush()
+                        img = np.ascontiguousarray(self.O.stb_decode(t.name))      # the reference's own decoder
+                    assert img.shape[:2] == (h, w)
+                    for _p in range(reserved):
+                        img = self.O.gray_inplace(img, ch, fma=bool(mode)) if ch == 3 else img
+                    out, off = img, (n + 4095) & ~4095
+                    n_out = out.nbytes
+                    if flags & WK_SHM:
+                        shm[off:off + n_out] = out.tobytes()
+                        c.sendall(REP.pack(MAGIC, 0, n_out, b""))
+                    else:
+                        c.sendall(REP.pack(MAGIC, 0, n_out, b"") + out.tobytes())
+                    continue
                 else:
                     out, off = self.O.sobel(np.frombuffer(data, np.uint8).reshape(h, w).copy(), np.zeros((h, w), np.uint8)), (n + 4095) & ~4095
                 if flags & WK_SHM:
@@ -326,3 +342,80 @@ def test_second_worker_does_not_steal_a_live_socket(real_worker):
     r = subprocess.run([str(WORKER), "--socket", str(real_worker)], capture_output=True, text=True, timeout=120)
     assert r.returncode != 0 and "another worker" in r.stderr
     assert run_client(real_worker, 3, 1).returncode == 0                       # the first worker still serves
+
+
+# ------------------------------------------------------------------------------------------------ the CLI with the codec steps replaced
+CLI = ROOT / "openmp-parallel-computing_b200" / "lib" / "ompimg_grayscale"
+
+
+def _png_pixels(path):
+    from PIL import Image
+    return np.ascontiguousarray(np.asarray(Image.open(path)))
+
+
+def test_cli_client_side_and_png_writer_against_a_fake_worker(O, golden, tmp_path):
+    """ompimg_grayscale (main.c's contract with decode and encode replaced) without a GPU: the JPEG goes to a fake worker that
+    answers with the reference's decoder + the oracle; the PNG this process writes must decode to the golden pixels."""
+    img = ROOT / "oracle" / "_ref" / "fixtures" / "test.jpg"
+    if not img.exists() or O.stb_decode(img) is None:
+        pytest.skip("reference image / stb_decode not on this box")
+    fw = FakeWorker(O, tmp_path / "w.sock")
+    try:
+        for passes, key in ((1, "golden_gray_sha256"), (3, "strict_p2_sha256")):
+            out = tmp_path / f"o{passes}.png"
+            r = subprocess.run([str(CLI), str(img), str(out), str(passes)], capture_output=True, text=True,
+                               env=dict(os.environ, OMPIMG_WORKER=str(tmp_path / "w.sock"), CUDA_VISIBLE_DEVICES="", OMPIMG_PNG_THREADS=str(passes)))
+            assert r.returncode == 0, r.stderr
+            assert r.stdout.startswith("Compute kernel \u00d7%d: " % passes) and r.stdout.rstrip().endswith(" s")
+            assert sha(_png_pixels(out)) == golden["test_jpg"][key]
+        assert [q[0] for q in fw.requests] == [4, 4]
+        assert fw.requests[0][5] == img.stat().st_size                  # the FILE travelled, not the pixels
+    finally:
+        fw.close()
+    # argv and error contract of main.c:15-25
+    r = subprocess.run([str(CLI)], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stderr.startswith("Uso: ")
+    r = subprocess.run([str(CLI), str(tmp_path / "missing.jpg"), str(tmp_path / "x.png")], capture_output=True, text=True)
+    assert r.returncode == 1 and "Errore caricando immagine" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_with_codec_steps_behind_the_real_worker(O, golden, real_worker, tmp_path):
+    """BASELINE config 1 end to end, the reference's real workload: `grayscale test.jpg out.png 1` as a whole process."""
+    fix = ROOT / "oracle" / "_ref" / "fixtures"
+    if not (fix / "test.jpg").exists():
+        pytest.skip("reference images did not travel")
+    env = dict(os.environ, OMPIMG_WORKER=str(real_worker), CUDA_VISIBLE_DEVICES="")
+
+    def run(exe, image, passes, e):
+        out = tmp_path / "o.png"
+        t0 = time.time()
+        r = subprocess.run([str(exe), str(fix / image), str(out), str(passes)], capture_output=True, text=True, env=e)
+        dt = time.time() - t0
+        assert r.returncode == 0, r.stderr
+        return _png_pixels(out), dt, r.stdout.strip()
+
+    px, t_first, _ = run(CLI, "test.jpg", 1, env)
+    assert sha(px) == golden["test_jpg"]["golden_gray_sha256"]
+    times = [run(CLI, "test.jpg", 1, env)[1] for _ in range(5)]
+    px3, _, line3 = run(CLI, "test.jpg", 3, env)
+    assert sha(px3) == golden["test_jpg"]["strict_p2_sha256"]
+    for name, key in (("more_than_one_mega_photo.jpg", "photo_jpg"), ("half_of_a_mega_photo.jpg", "half_jpg")):
+        if (fix / name).exists():
+            px, _, _ = run(CLI, name, 1, env)
+            rgb = O.stb_decode(fix / name)
+            assert np.array_equal(px, O.gray_inplace(np.ascontiguousarray(rgb), 3))
+    ref = ROOT / "oracle" / "_ref" / "bin" / "grayscale_strict"
+    msg = f"\nompimg_grayscale test.jpg x1 behind the worker: first {t_first:.3f} s, then {min(times):.3f}..{max(times):.3f} s (median {sorted(times)[2]:.3f}) [{line3}]"
+    if ref.exists():
+        ref_times = []
+        for _ in range(5):
+            out = tmp_path / "r.png"
+            t0 = time.time()
+            assert subprocess.run([str(ref), str(fix / "test.jpg"), str(out), "1"], capture_output=True, env=dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count()))).returncode == 0
+            ref_times.append(time.time() - t0)
+        msg += f" | reference CLI (all host threads): {min(ref_times):.3f}..{max(ref_times):.3f} s (median {sorted(ref_times)[2]:.3f})"
+        assert sha(_png_pixels(tmp_path / "r.png")) == golden["test_jpg"]["golden_gray_sha256"]
+    print(msg)
+    (ROOT / "gpurun_out").mkdir(exist_ok=True)
+    (ROOT / "gpurun_out" / "cli_codec_times.txt").write_text(msg.strip() + "\n")
