@@ -729,20 +729,26 @@ def other_kernels(pkg, L, peak, with_cpu=True):
     out["gray_sobel_pass_rgb_inplace_3840x2160x64"] = entry(n5 * PX, 6, sec)
     out["gray_sobel_pass_rgb_inplace_3840x2160x64"]["launches_per_pass"] = (pkg.launch_count() - l0) / 13
     img.free(); e.free()
-    # cfg4: 8192x8192 RGB box / binomial blur (uint8 out)
+    # cfg4: 8192x8192 RGB box / binomial blur (uint8 out).  Device layout: rows 128-byte aligned like every device copy the host entry
+    # points make (conv_tma.cuh: tensor-map copies); the reference's dense (cols+K-1)*3 pitch (conv_sep.cuh) is timed beside it.
     rows = cols = 8192
     for K in (5, 9):
         pr, pc = rows + K - 1, cols + K - 1
-        src = pkg.DeviceBuffer(pr * pc * 3); dst = pkg.DeviceBuffer(rows * cols * 3)
+        ip = (pc * 3 + 127) // 128 * 128
+        src = pkg.DeviceBuffer(pr * ip); dst = pkg.DeviceBuffer(rows * cols * 3)
         pkg.synth_dev(src, src.nbytes, 4)
         taps = np.ones(K * K, np.int32)
-        out[f"conv_box{K}x{K}_8192x8192"] = entry(rows * cols, 6, timeit(lambda: L.ompimg_conv_u8_dev(src.ptr, pc * 3, rows, cols, K, taps.ctypes.data, K * K, dst.ptr, cols * 3, 0), 5))
-        out[f"conv_box{K}x{K}_8192x8192"]["cpu"] = partner("conv", sorted({1, cores}), K=K)
         bn = np.array([1.0])
         for _ in range(K - 1):
             bn = np.convolve(bn, [1, 1])
         g = np.outer(bn, bn).astype(np.int32).ravel().copy()
-        out[f"conv_binomial{K}x{K}_8192x8192"] = entry(rows * cols, 6, timeit(lambda: L.ompimg_conv_u8_dev(src.ptr, pc * 3, rows, cols, K, g.ctypes.data, int(g.sum()), dst.ptr, cols * 3, 0), 5))
+        for name, tp, nm in (("box", taps, K * K), ("binomial", g, int(g.sum()))):
+            key = f"conv_{name}{K}x{K}_8192x8192"
+            out[key] = entry(rows * cols, 6, timeit(lambda: L.ompimg_conv_u8_dev(src.ptr, ip, rows, cols, K, tp.ctypes.data, nm, dst.ptr, cols * 3, 0), 10))
+            out[key]["in_pitch"] = ip
+            out[key]["dense_pitch"] = entry(rows * cols, 6, timeit(lambda: L.ompimg_conv_u8_dev(src.ptr, pc * 3, rows, cols, K, tp.ctypes.data, nm, dst.ptr, cols * 3, 0), 10))
+            out[key]["dense_pitch"]["in_pitch"] = pc * 3
+        out[f"conv_box{K}x{K}_8192x8192"]["cpu"] = partner("conv", sorted({1, cores}), K=K)
         src.free(); dst.free()
     # a7: channel sums, 8192x8192
     src = pkg.DeviceBuffer(rows * cols * 3); sums = pkg.DeviceBuffer(64)

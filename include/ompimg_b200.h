@@ -206,6 +206,13 @@ OMPIMG_API int  ompimg_bands_upload(ompimg_bands *b, const uint8_t *rgb_host);  
 OMPIMG_API int  ompimg_bands_rgb_to_edge(ompimg_bands *b, float *ms_max);           /* gray+Sobel on every band, halo via peer access */
 OMPIMG_API int  ompimg_bands_download_edge(ompimg_bands *b, uint8_t *edge_host);    /* dense width*height plane, border bytes untouched */
 OMPIMG_API int  ompimg_bands_checksum(ompimg_bands *b, unsigned long long *sum);    /* sum of all interior edge bytes */
+/* a6 over bands (old/parallel_convolution.c:12-23): the banded 3-channel image is the pre-padded input, the output is
+ * (height-K+1) x (width-K+1) x 3 uint8 with row r on the device that holds input row r.  The K-1 input rows below a band are
+ * copied from the next device(s) over NVLink (cudaMemcpyPeerAsync) before the band's kernel starts: one exchange step. */
+OMPIMG_API int  ompimg_bands_conv_u8(ompimg_bands *b, int K, const int32_t *taps, int32_t norm, float *ms_max);
+OMPIMG_API int  ompimg_bands_download_conv(ompimg_bands *b, uint8_t *out_host);     /* dense (height-K+1) x (width-K+1) x 3 */
+/* a7 over bands (old/parallel_avg_pixel.c:17-30): per-device partial channel sums, added on the host */
+OMPIMG_API int  ompimg_bands_channel_sums(ompimg_bands *b, unsigned long long *sums3, float *ms_max);
 
 /* one process per GPU (the launcher's form: torchrun, mpirun): the band above / below is another process's
  * allocation.  ompimg_ipc_export writes the 64-byte CUDA IPC handle of a buffer from ompimg_dev_alloc; the

@@ -114,6 +114,9 @@ _SIGS = {
     "ompimg_bands_rgb_to_edge": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "ompimg_bands_download_edge": (C.c_int, [_vp, _vp]),
     "ompimg_bands_checksum": (C.c_int, [_vp, C.POINTER(C.c_ulonglong)]),
+    "ompimg_bands_conv_u8": (C.c_int, [_vp, C.c_int, _vp, C.c_int32, C.POINTER(C.c_float)]),
+    "ompimg_bands_download_conv": (C.c_int, [_vp, _vp]),
+    "ompimg_bands_channel_sums": (C.c_int, [_vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_float)]),
     "ompimg_jpeg_probe": (C.c_int, [_vp, _sz, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ompimg_jpeg_parse": (_vp, [_vp, _sz]),
     "ompimg_jpeg_free": (None, [_vp]),
@@ -477,6 +480,28 @@ class Bands:
         s = C.c_ulonglong()
         _ck(lib().ompimg_bands_checksum(self.h_, C.byref(s)), "bands_checksum")
         return int(s.value)
+
+    def convolution(self, kernel: np.ndarray, norm: int) -> float:
+        """a6 over the bands (old/parallel_convolution.c:12-23): the banded image is the pre-padded input; returns the device ms"""
+        k = np.ascontiguousarray(kernel, np.int32)
+        if k.ndim != 2 or k.shape[0] != k.shape[1]:
+            raise OmpimgError("kernel must be K x K")
+        ms = C.c_float()
+        _ck(lib().ompimg_bands_conv_u8(self.h_, k.shape[0], k.ctypes.data, int(norm), C.byref(ms)), "bands_conv_u8")
+        self.k_ = k.shape[0]
+        return float(ms.value)
+
+    def download_convolution(self) -> np.ndarray:
+        out = np.zeros((self.h - self.k_ + 1, self.w - self.k_ + 1, 3), np.uint8)
+        _ck(lib().ompimg_bands_download_conv(self.h_, _ptr(out)), "bands_download_conv")
+        return out
+
+    def channel_sums(self):
+        """a7 over the bands (old/parallel_avg_pixel.c:17-30): per-device partial sums added on the host; (sums[3], device ms)"""
+        s3 = (C.c_ulonglong * 3)()
+        ms = C.c_float()
+        _ck(lib().ompimg_bands_channel_sums(self.h_, s3, C.byref(ms)), "bands_channel_sums")
+        return [int(v) for v in s3], float(ms.value)
 
     def close(self):
         if self.h_:

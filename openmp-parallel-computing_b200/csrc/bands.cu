@@ -53,6 +53,8 @@ cudaError_t launch_byte_sum(const uint8_t *src, size_t pitch, int width, int row
 
 }  // namespace ompimg
 
+constexpr int BANDS_TAIL_ROWS = 14;   // K <= 15
+
 struct ompimg_bands {
     int w, h, ch, ndev;
     int dev[16];
@@ -62,6 +64,8 @@ struct ompimg_bands {
     uint8_t *rgb[16];
     uint8_t *edge[16];
     uint8_t *halo[16];          // 2 rows (above, below) when peer access is unavailable
+    uint8_t *conv[16];          // convolution output of the band (allocated by the first ompimg_bands_conv_u8)
+    size_t cpitch; int conv_k;  // its pitch and the K it was sized for
     unsigned long long *sum[16];
     bool direct[16][2];         // can device i read its (above, below) neighbour directly?
     cudaStream_t st[16];
@@ -96,7 +100,7 @@ extern "C" ompimg_bands *ompimg_bands_create(int w, int h, int ch, int ndev, con
         if (b->dev[i] < 0 || b->dev[i] >= count) { ok = false; break; }
         const int rows = b->row0[i + 1] - b->row0[i];
         ok = cudaSetDevice(b->dev[i]) == cudaSuccess &&
-             cudaMalloc(&b->rgb[i], b->rpitch * rows) == cudaSuccess &&
+             cudaMalloc(&b->rgb[i], b->rpitch * (rows + BANDS_TAIL_ROWS)) == cudaSuccess &&        // + room for the K-1 rows below (convolution)
              cudaMalloc(&b->edge[i], b->epitch * rows) == cudaSuccess &&
              cudaMalloc(&b->halo[i], 2 * b->rpitch) == cudaSuccess &&
              cudaMalloc(&b->sum[i], 8) == cudaSuccess &&
@@ -132,7 +136,7 @@ extern "C" int ompimg_bands_destroy(ompimg_bands *b) {
         if (b->st[i]) { cudaStreamSynchronize(b->st[i]); cudaStreamDestroy(b->st[i]); }
         if (b->e0[i]) cudaEventDestroy(b->e0[i]);
         if (b->e1[i]) cudaEventDestroy(b->e1[i]);
-        cudaFree(b->rgb[i]); cudaFree(b->edge[i]); cudaFree(b->halo[i]); cudaFree(b->sum[i]);
+        cudaFree(b->rgb[i]); cudaFree(b->edge[i]); cudaFree(b->halo[i]); cudaFree(b->sum[i]); cudaFree(b->conv[i]);
     }
     cudaGetLastError();
     cudaSetDevice(b->home);
@@ -275,6 +279,108 @@ extern "C" int ompimg_bands_checksum(ompimg_bands *b, unsigned long long *sum) {
     BCK(cudaSetDevice(b->home));
     *sum = total;
     return OMPIMG_OK;
+}
+
+// ---- row-band forms of the old/ kernels ------------------------------------------------------------------------
+// a6 (old/parallel_convolution.c:12-23) over bands.  The banded image is the reference's pre-padded, top-left anchored input:
+// output row r needs input rows r .. r+K-1, so a band needs the K-1 rows BELOW it, which live in the next device's band (or
+// in several, when bands are shorter than K-1 rows).  They are copied over NVLink into the tail of this band's buffer with
+// cudaMemcpyPeerAsync (P2P, no host staging) on the band's stream, then the band's convolution runs on its device: one
+// exchange step, no collective.  Output row r stays on the device that holds input row r.
+static int bands_conv_enqueue(ompimg_bands *b, int i, int K, const int32_t *taps, int32_t norm) {
+    BCK(cudaSetDevice(b->dev[i]));
+    const int rows = b->row0[i + 1] - b->row0[i];
+    const int out_h = b->h - K + 1, out_w = b->w - K + 1;
+    const int nout = (b->row0[i + 1] < out_h ? b->row0[i + 1] : out_h) - b->row0[i];
+    BCK(cudaEventRecord(b->e0[i], b->st[i]));
+    if (nout > 0) {
+        const int need_end = b->row0[i] + nout + K - 1;                 // one past the last input row of this band's outputs
+        for (int j = i + 1; j < b->ndev && b->row0[j] < need_end; ++j) {
+            const int r0 = b->row0[j], r1 = b->row0[j + 1] < need_end ? b->row0[j + 1] : need_end;
+            uint8_t *dst = b->rgb[i] + (size_t)(r0 - b->row0[i]) * b->rpitch;
+            if (b->dev[j] == b->dev[i]) BCK(cudaMemcpyAsync(dst, b->rgb[j], (size_t)(r1 - r0) * b->rpitch, cudaMemcpyDeviceToDevice, b->st[i]));
+            else BCK(cudaMemcpyPeerAsync(dst, b->dev[i], b->rgb[j], b->dev[j], (size_t)(r1 - r0) * b->rpitch, b->st[i]));
+        }
+        BCK(launch_conv(b->rgb[i], b->rpitch, nout, out_w, K, taps, norm, b->conv[i], b->cpitch, 1, b->sm_count[i], b->st[i]));
+    }
+    (void)rows;
+    BCK(cudaEventRecord(b->e1[i], b->st[i]));
+    return OMPIMG_OK;
+}
+
+static int bands_collect_ms(ompimg_bands *b, float *ms_max) {
+    float mx = 0.f;
+    for (int i = 0; i < b->ndev; ++i) {
+        BCK(cudaSetDevice(b->dev[i]));
+        BCK(cudaEventSynchronize(b->e1[i]));
+        float ms = 0.f;
+        BCK(cudaEventElapsedTime(&ms, b->e0[i], b->e1[i]));
+        if (ms > mx) mx = ms;
+    }
+    BCK(cudaSetDevice(b->home));
+    if (ms_max) *ms_max = mx;
+    return OMPIMG_OK;
+}
+
+extern "C" int ompimg_bands_conv_u8(ompimg_bands *b, int K, const int32_t *taps, int32_t norm, float *ms_max) {
+    if (!b || !taps || b->ch != 3 || K < 1 || K > BANDS_TAIL_ROWS + 1 || norm == 0 || b->w < K || b->h < K) return OMPIMG_ERR_ARG;
+    const size_t cpitch = ((size_t)(b->w - K + 1) * 3 + 127) / 128 * 128;
+    if (!b->conv[0] || b->conv_k != K) {
+        for (int i = 0; i < b->ndev; ++i) {
+            BCK(cudaSetDevice(b->dev[i]));
+            if (b->conv[i]) { BCK(cudaFree(b->conv[i])); b->conv[i] = nullptr; }
+            BCK(cudaMalloc(&b->conv[i], cpitch * (size_t)(b->row0[i + 1] - b->row0[i])));
+        }
+        b->cpitch = cpitch; b->conv_k = K;
+    }
+    int rcs[16] = {};
+    if (b->ndev > 1) {
+        std::vector<std::thread> th;
+        for (int i = 0; i < b->ndev; ++i) th.emplace_back([&, i] { rcs[i] = bands_conv_enqueue(b, i, K, taps, norm); });
+        for (auto &t : th) t.join();
+    } else {
+        rcs[0] = bands_conv_enqueue(b, 0, K, taps, norm);
+    }
+    for (int i = 0; i < b->ndev; ++i) if (rcs[i]) return rcs[i];
+    return bands_collect_ms(b, ms_max);
+}
+
+extern "C" int ompimg_bands_download_conv(ompimg_bands *b, uint8_t *out_host) {
+    if (!b || !out_host || !b->conv[0]) return OMPIMG_ERR_ARG;
+    const int K = b->conv_k, out_h = b->h - K + 1;
+    const size_t row = (size_t)(b->w - K + 1) * 3;
+    for (int i = 0; i < b->ndev; ++i) {
+        BCK(cudaSetDevice(b->dev[i]));
+        const int y0 = b->row0[i], y1 = b->row0[i + 1] < out_h ? b->row0[i + 1] : out_h;
+        if (y1 <= y0) continue;
+        BCK(cudaMemcpy2DAsync(out_host + row * y0, row, b->conv[i], b->cpitch, row, y1 - y0, cudaMemcpyDeviceToHost, b->st[i]));
+    }
+    return bands_sync(b);
+}
+
+// a7 (old/parallel_avg_pixel.c:17-30) over bands: every device sums its band (partial sums), the host adds the ndev triples --
+// 24 bytes per device, the reduction the reference does with its `reduction(+:avgs)` clause.
+extern "C" int ompimg_bands_channel_sums(ompimg_bands *b, unsigned long long *sums3, float *ms_max) {
+    if (!b || !sums3 || b->ch != 3) return OMPIMG_ERR_ARG;
+    unsigned long long *acc[16] = {};
+    for (int i = 0; i < b->ndev; ++i) {
+        BCK(cudaSetDevice(b->dev[i]));
+        BCK(cudaMalloc(&acc[i], 32));
+        BCK(cudaMemsetAsync(acc[i], 0, 32, b->st[i]));
+        BCK(cudaEventRecord(b->e0[i], b->st[i]));
+        BCK(launch_channel_sums(b->rgb[i], b->rpitch, b->row0[i + 1] - b->row0[i], b->w, acc[i], b->sm_count[i], b->st[i]));
+        BCK(cudaEventRecord(b->e1[i], b->st[i]));
+    }
+    sums3[0] = sums3[1] = sums3[2] = 0;
+    for (int i = 0; i < b->ndev; ++i) {
+        BCK(cudaSetDevice(b->dev[i]));
+        unsigned long long part[3] = {};
+        BCK(cudaMemcpyAsync(part, acc[i], 24, cudaMemcpyDeviceToHost, b->st[i]));
+        BCK(cudaStreamSynchronize(b->st[i]));
+        for (int c = 0; c < 3; ++c) sums3[c] += part[c];
+        BCK(cudaFree(acc[i]));
+    }
+    return bands_collect_ms(b, ms_max);
 }
 
 // ---- one process per GPU: the neighbour's band is another PROCESS's allocation --------------------------------

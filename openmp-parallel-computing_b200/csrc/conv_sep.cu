@@ -1,8 +1,12 @@
 // conv_sep.cu -- host side of the rank-1 convolution path: range checks, tap words, launch geometry.
-// The kernel is in conv_sep.cuh, instantiated per K in conv_sep_k{3,5,7,9}.cu.
+// Two kernels with the same arithmetic: conv_tma.cuh (16-byte aligned base and pitch: warp-autonomous, tensor-map copies;
+// instantiated per K in conv_tma_k{3,5,7,9}.cu) and conv_sep.cuh (any 4-byte aligned layout, e.g. the reference's dense
+// (cols+K-1)*3 pitch: producer warp + 1-D bulk copies; conv_sep_k{3,5,7,9}.cu).
 #include <cstdlib>
 
 #include "conv_sep.cuh"
+#include "conv_tma.cuh"
+#include "tma.h"
 
 namespace ompimg {
 
@@ -60,13 +64,7 @@ bool launch_conv_sep(const uint8_t *in, size_t in_pitch, int rows, int cols, int
         }
     }
 
-    ConvSepParams p{};
-    p.in = in; p.out = reinterpret_cast<uint8_t *>(out); p.in_pitch = in_pitch; p.out_pitch = out_pitch;
-    p.in_end = in + (size_t)(rows + K - 2) * in_pitch + (size_t)in_row;
-    p.rows = rows; p.cols = cols;
-    p.in_row_bytes = (uint32_t)in_row;
-    p.magic = magic; p.shift = shift; p.norm = norm;
-    p.out_wide = (((uintptr_t)out | out_pitch) & 15) == 0;
+    uint32_t th[4][3], ut[5];
     for (int i = 0; i < 4; ++i)
         for (int m = 0; m < 3; ++m) {
             uint32_t wv = 0;
@@ -74,10 +72,50 @@ bool launch_conv_sep(const uint8_t *in, size_t in_pitch, int rows, int cols, int
                 const int k = 4 * m + b - i;
                 if (k >= 0 && k < K) wv |= (uint32_t)(vv[k] & 255) << (8 * b);
             }
-            p.th[i][m] = wv;
+            th[i][m] = wv;
         }
     auto ub = [&](int k) -> uint32_t { return k >= 0 && k < K ? (uint32_t)(u[k] & 255) : 0u; };
-    for (int q = 0; q < 5; ++q) p.ut[q] = ub(2 * q) | ub(2 * q + 1) << 8 | ub(2 * q - 1) << 16 | ub(2 * q) << 24;
+    for (int q = 0; q < 5; ++q) ut[q] = ub(2 * q) | ub(2 * q + 1) << 8 | ub(2 * q - 1) << 16 | ub(2 * q) << 24;
+
+    // ---- 16-byte aligned base and pitch, unsigned taps: the warp-autonomous kernel fed by tensor-map copies (conv_tma.cuh)
+    static int tma_env = -1;
+    if (tma_env < 0) { const char *e = getenv("OMPIMG_CONV_TMA"); tma_env = e ? atoi(e) : 1; }
+    const unsigned long long in_row8 = (in_row + 7ull) & ~7ull;
+    if (tma_env && div != 2 && (((uintptr_t)in | in_pitch) & 15) == 0 && in_pitch >= in_row8) {
+        if (EncodeTiledFn enc = encode_tiled_fn()) {
+            ConvTmaParams q{};
+            const cuuint64_t dims[2] = {in_row8 / 8, (cuuint64_t)(rows + K - 1)};
+            const cuuint64_t strides[1] = {in_pitch};
+            const cuuint32_t box[2] = {ct_box_bytes(K) / 8, 2}, estr[2] = {1, 1};
+            if (enc(&q.map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<uint8_t *>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+                q.out = reinterpret_cast<uint8_t *>(out); q.out_pitch = out_pitch;
+                q.rows = rows; q.cols = cols;
+                q.nstrips = (cols + CT_WPX - 1) / CT_WPX;
+                q.out_wide = (((uintptr_t)out | out_pitch) & 15) == 0;
+                for (int i = 0; i < 4; ++i) for (int m = 0; m < 3; ++m) q.th[i][m] = th[i][m];
+                for (int k = 0; k < 5; ++k) q.ut[k] = ut[k];
+                q.magic = magic; q.shift = shift;
+                switch (K) {
+                    case 3: *err = launch_conv_tma_k<3>(q, out_is_u8, div, vbox, sm_count, st); break;
+                    case 5: *err = launch_conv_tma_k<5>(q, out_is_u8, div, vbox, sm_count, st); break;
+                    case 7: *err = launch_conv_tma_k<7>(q, out_is_u8, div, vbox, sm_count, st); break;
+                    default: *err = launch_conv_tma_k<9>(q, out_is_u8, div, vbox, sm_count, st); break;
+                }
+                return true;
+            }
+        }
+    }
+
+    ConvSepParams p{};
+    p.in = in; p.out = reinterpret_cast<uint8_t *>(out); p.in_pitch = in_pitch; p.out_pitch = out_pitch;
+    p.in_end = in + (size_t)(rows + K - 2) * in_pitch + (size_t)in_row;
+    p.rows = rows; p.cols = cols;
+    p.in_row_bytes = (uint32_t)in_row;
+    p.magic = magic; p.shift = shift; p.norm = norm;
+    p.out_wide = (((uintptr_t)out | out_pitch) & 15) == 0;
+    for (int i = 0; i < 4; ++i) for (int m = 0; m < 3; ++m) p.th[i][m] = th[i][m];
+    for (int q = 0; q < 5; ++q) p.ut[q] = ut[q];
 
     p.nw = min(CS_NW, (cols + CS_WPX - 1) / CS_WPX);
     const int SW = p.nw * CS_WPX;

@@ -1,0 +1,399 @@
+// conv_tma.cuh -- K x K convolution with rank-1 taps on interleaved uint8 RGB, warp-autonomous form:
+// the fast path of a6 (old/parallel_convolution.c:8-24) for inputs whose base and pitch are 16-byte
+// aligned (every device copy the host entry points make; conv_sep.cuh keeps the dense-pitch layouts).
+// Same results as conv.cu / conv_sep.cuh: out[r][c][p] = (sum_{kr,kc} in[r+kr][c+kc][p] * u[kr]*v[kc]) / norm,
+// C division, no clamp, pre-padded top-left anchored input.  One translation unit per K (conv_tma_k*.cu).
+//
+// Data movement.  Every WARP is its own pipeline (as in stencil.cu): it owns a band of output rows x a
+// strip of 128 pixels, runs a private ring of two-row stages with one mbarrier per stage, and an elected
+// lane requests a whole stage with ONE cp.async.bulk.tensor.2d (SASS UTMALDG): box = {(128+K-1)*3 bytes
+// rounded up to 16, 2 rows} of the tensor {row bytes, rows+K-1}.  Parts of a box right of the row or
+// below the image are zero-filled by the copy engine, so the kernel holds no address arithmetic for its
+// loads, no clamping and no dummy rows.  There is no producer warp, no empty barrier and no CTA-wide
+// barrier (conv_sep.cuh: 4.0 % SYNCS + 3.4 % NANOSLEEP of all instructions, a fifth of the CTA's warps,
+// and consumers that wait for the slowest of four warps to release a stage).
+//
+// Loop structure.  A band's trips (two input rows each) run in blocks of NP = (K+1)/2 trips, so that the
+// ring slot of the vertical window is a compile-time register.  The first block (K-1 priming rows, first
+// outputs) and the last trips of the band run a "checked" body; every block in between runs a body with
+// no per-trip tests (emit, second-row-valid, trip-exists).
+//
+// Arithmetic per lane (4 pixels = 12 output bytes) and input row: identical to conv_sep.cuh --
+//   1. de-interleave: 2 PRMT per planar word;
+//   2. horizontal pass: ceil((K+3)/4) IDP.4A per value against host-shifted tap words;
+//   3. vertical pass: general u: IDP.2A over u16 row pairs in a register ring; constant u (box blur):
+//      running window sums of u16 column pairs, one IADD3 per pair and row;
+//   4. division: shift | multiply-high | byte select (norm 256 / 65536).
+// Instruction budget and the pipe that bounds each K: DESIGN.md 4.3.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ompimg {
+
+#ifndef CT_MINB_LO
+#define CT_MINB_LO 5                     // resident CTAs per SM the K <= 5 kernels are compiled for
+#endif
+#ifndef CT_MINB_HI
+#define CT_MINB_HI 4                     // ... and the K >= 7 kernels
+#endif
+constexpr int CT_WARPS = 4;              // warps (tasks) per CTA
+constexpr int CT_LPX = 4;                // output pixels per lane
+constexpr int CT_WPX = 32 * CT_LPX;      // output pixels per warp and row
+
+constexpr uint32_t ct_box_bytes(int K) { return (uint32_t)(((CT_WPX + K - 1) * 3 + 15) & ~15); }
+constexpr uint32_t ct_stage_bytes(int K) { return (2 * ct_box_bytes(K) + 127u) & ~127u; }
+
+struct ConvTmaParams {
+    CUtensorMap map;             // {ceil(row bytes / 8), rows+K-1} of uint64 elements, box {box bytes / 8, 2}
+    uint8_t *out;
+    size_t out_pitch;
+    int rows, cols;
+    int band_rows;               // even
+    int nstrips;
+    long long ntasks;            // nbands * nstrips, one task per warp
+    int stages;                  // ring depth per warp (>= 2)
+    uint32_t out_wide;           // output rows are 16-byte aligned: 128-bit stores through the staging buffer
+    uint32_t th[4][3];           // horizontal tap words
+    uint32_t ut[5];              // vertical tap-pair words: bytes (u[2q], u[2q+1], u[2q-1], u[2q])
+    uint32_t magic;
+    int32_t shift;
+};
+
+// band geometry is chosen by the launcher from the kernel's occupancy (conv_tma.cu passes everything else)
+template <int K>
+cudaError_t launch_conv_tma_k(ConvTmaParams &p, int out_u8, int div, int vbox, int sm_count, cudaStream_t st);
+
+#ifdef OMPIMG_CONV_TMA_IMPL
+
+__device__ __forceinline__ bool ct_elect() {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+template <bool HI>
+__device__ __forceinline__ uint32_t ct_dp2(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    if (HI) asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    else asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t ct_dp4(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+template <int N> struct CtInt { static constexpr int value = N; };
+template <bool B> struct CtBool { static constexpr bool value = B; };
+
+// DIV: 0 acc >> shift | 1 umulhi(acc, magic) | 3 byte 1 (norm 256, u8 out) | 4 byte 2 (norm 65536, u8 out); taps >= 0.
+// VBOX (DIV 0 or 1 only): constant vertical taps, running window sums.
+template <int K, bool OUT_U8, int DIV, bool VBOX>
+__global__ void __launch_bounds__(CT_WARPS * 32, K <= 5 ? CT_MINB_LO : (VBOX ? CT_MINB_HI : CT_MINB_HI + 1)) conv_tma_kernel(const __grid_constant__ ConvTmaParams p) {
+    constexpr int NP = (K + 1) / 2;                 // trips per block; pair-rows in the vertical window
+    constexpr int NPX = CT_LPX + K - 1;             // input pixels per lane
+    constexpr int NWRD = (NPX * 3 + 3) / 4;         // 32-bit words that hold them
+    constexpr int NG = (NPX + 3) / 4;               // planar words per channel
+    constexpr int OB = OUT_U8 ? 1 : 4;
+    constexpr uint32_t WROW = CT_WPX * 3 * OB;      // staging bytes per output row
+    constexpr int RING = VBOX ? (K + 1) * 6 : NP * 12;
+    constexpr uint32_t BOXB = ct_box_bytes(K), STAGE = ct_stage_bytes(K);
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);           // warp-uniform by construction
+    const long long task = (long long)blockIdx.x * CT_WARPS + warp;
+    if (task >= p.ntasks) return;                   // warps are independent: no CTA-wide barrier below
+    // strip-major inside a band: the warps of a CTA read one contiguous piece of every row
+    const int band = (int)(task / p.nstrips), strip = (int)(task - (long long)band * p.nstrips);
+    const int S = p.stages;
+    const uint32_t warp_bytes = (uint32_t)S * STAGE + 2u * WROW;
+    const uint32_t base = (smem_u32(smem) + 127u) & ~127u;
+    const uint32_t ring0 = base + (uint32_t)warp * warp_bytes;
+    const uint32_t staging0 = ring0 + (uint32_t)S * STAGE;
+    const uint32_t bar0 = base + CT_WARPS * warp_bytes + (uint32_t)warp * (8u * (uint32_t)S);
+
+    const int xs = strip * CT_WPX;
+    const int ya = band * p.band_rows, yb = min(p.rows, ya + p.band_rows);
+    const int nout = yb - ya;
+    const int ntrips = (nout + K) >> 1;             // input rows ya .. yb+K-2, two per trip (a missing last row is zero-filled)
+
+    if (lane == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(bar0 + 8 * s, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    const int cx = xs * 3 / 8;                      // box start in uint64 elements (384 bytes per strip)
+    auto request = [&](uint32_t stage_off, uint32_t bar, int tt) {                 // elected lane only
+        mbar_expect_tx(bar, 2u * BOXB);
+        tma_load_2d(ring0 + stage_off, &p.map, cx, ya + 2 * tt, bar);
+    };
+    if (ct_elect()) {
+        for (int t = 0; t < S && t < ntrips; ++t) request((uint32_t)t * STAGE, bar0 + 8 * t, t);
+    }
+
+    const int seg0 = xs * 3;                                                    // first output byte column of the warp
+    const int nval = max(0, min(CT_WPX * 3, p.cols * 3 - seg0));                 // valid output byte columns of the warp
+    const bool wide = p.out_wide && nval == CT_WPX * 3;
+    const int lval = nval - lane * 12;                                          // valid output values of the lane (<= 0: none)
+    const uint32_t my = keep(ring0 + (uint32_t)lane * (CT_LPX * 3u));
+    const uint32_t ring_bytes = (uint32_t)S * STAGE;
+    // staging: two output rows per warp; written as 12 values per lane, read back as 16-byte pieces
+    // (piece c = lane + 32*j lies in row c / PPR at byte (c % PPR) * 16; j < NPC)
+    constexpr int PPR = (int)WROW / 16, NPC = 2 * PPR / 32 + (2 * PPR % 32 ? 1 : 0);
+    const uint32_t stg = staging0 + (uint32_t)lane * (12u * OB);
+    const uint32_t stg_rd = staging0 + (uint32_t)lane * 16u;
+    const size_t opitch = p.out_pitch;
+    uint8_t *orow = p.out + (size_t)ya * opitch + (size_t)seg0 * OB;            // next output row of this warp
+    int ro = ya;
+
+    uint32_t W[RING];            // VBOX: P[slot][6] (slot = input row mod K+1); else W[pair-row slot][12]
+#pragma unroll
+    for (int q = 0; q < RING; ++q) W[q] = 0u;
+    uint32_t SUM[6];             // VBOX: running window sums, two columns per register
+#pragma unroll
+    for (int q = 0; q < 6; ++q) SUM[q] = 0u;
+
+    uint32_t so = 0, fb = bar0, ph = 0;            // ring position (stage offset, its barrier, its phase) of the next trip
+    int t0 = 0;                                    // trip number of the current block's first trip
+
+    // one trip: slot s_c of the current block.  CHECKED: the trip may not exist, may not emit (priming), may hold one output row only.
+    auto trip = [&](auto s_c, auto checked_c) __attribute__((always_inline)) {
+        constexpr int s = decltype(s_c)::value;
+        constexpr bool CHECKED = decltype(checked_c)::value;
+        const int t = t0 + s;
+        if (CHECKED && t >= ntrips) return;
+        mbar_wait(fb, ph);
+        uint32_t w[2][NWRD];
+#pragma unroll
+        for (int rho = 0; rho < 2; ++rho) {
+            const uint32_t a = my + so + (uint32_t)rho * BOXB;
+#pragma unroll
+            for (int i = 0; i < NWRD; ++i) w[rho][i] = lds32(a + 4 * i);
+        }
+        __syncwarp();                                  // every lane holds both rows (and has read the previous trip's staging rows)
+        if (ct_elect() && t + S < ntrips) request(so, fb, t + S);
+        so += STAGE; fb += 8;
+        if (so == ring_bytes) { so = 0; fb = bar0; ph ^= 1; }
+
+        const bool emit = !CHECKED || t >= NP - 1;
+        const bool two = !CHECKED || ro + 1 < yb;
+        uint32_t h[2][12];
+#pragma unroll
+        for (int rho = 0; rho < 2; ++rho) {
+            // planar words: X[ch][m] = channel ch of pixels 4m .. 4m+3 (pixels past NPX meet zero taps)
+            uint32_t X[3][NG];
+#pragma unroll
+            for (int m = 0; m < NG; ++m) {
+                const uint32_t wa = w[rho][3 * m];
+                const uint32_t wb = 3 * m + 1 < NWRD ? w[rho][3 * m + 1] : 0u;
+                X[0][m] = prmt(wa, wb, 0x0630);     // r0 r1 r2 .
+                X[1][m] = prmt(wa, wb, 0x0741);     // g0 g1 g2 .
+                X[2][m] = prmt(wa, wb, 0x0052);     // b0 b1 . .
+                if (3 * m + 2 < NWRD) {
+                    const uint32_t wc = w[rho][3 * m + 2];
+                    X[0][m] = prmt(X[0][m], wc, 0x5210);   // r3 = wc.b1
+                    X[1][m] = prmt(X[1][m], wc, 0x6210);   // g3 = wc.b2
+                    X[2][m] = prmt(X[2][m], wc, 0x7410);   // b2 = wc.b0, b3 = wc.b3
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t acc = 0u;
+#pragma unroll
+                    for (int m = 0; m < NG; ++m)
+                        if (4 * m + 3 - i >= 0 && 4 * m - i < K) acc = ct_dp4(X[ch][m], p.th[i][m < 3 ? m : 0], acc);
+                    h[rho][ch * 4 + i] = acc;
+                }
+        }
+        if (!VBOX) {
+#pragma unroll
+            for (int c = 0; c < 12; ++c) W[s * 12 + c] = prmt(h[0][c], h[1][c], 0x5410);
+        }
+
+        // value j of the lane (byte column 12*lane + j) is pixel j/3, channel j%3: column index (j%3)*4 + j/3
+#define CT_COL(j) (((j) % 3) * 4 + (j) / 3)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            // Y[c]: the quotient of column c, in byte YB of the register (u8 output) or shifted down (int32 output)
+            uint32_t Y[12];
+            constexpr int YB = VBOX ? (DIV == 1 ? 2 : 0) : DIV == 3 ? 1 : DIV == 4 ? 2 : 0;
+            if (VBOX) {
+                // window sums of the K newest rows: S += P[row] - P[row-K], two columns per IADD3
+                constexpr int R = K + 1;
+                constexpr int slot_base = 2 * s;
+                const int slot = slot_base + half, old = (slot_base + half + 1) % R;
+#pragma unroll
+                for (int pc = 0; pc < 6; ++pc) {
+                    const uint32_t pn = prmt(h[half][2 * pc], h[half][2 * pc + 1], 0x5410);
+                    SUM[pc] = SUM[pc] + pn - W[old * 6 + pc];
+                    W[slot * 6 + pc] = pn;
+                }
+                if (emit) {
+#pragma unroll
+                    for (int pc = 0; pc < 6; ++pc) {
+                        if (DIV == 1) {
+                            // floor(s/norm) sits in bits 16.. of umulhi(s << 16 | anything below, magic) (host-checked range)
+                            Y[2 * pc + 1] = __umulhi(SUM[pc], p.magic);
+                            Y[2 * pc] = __umulhi(SUM[pc] << 16, p.magic);
+                            if (!OUT_U8) { Y[2 * pc + 1] >>= 16; Y[2 * pc] >>= 16; }
+                        } else {
+                            Y[2 * pc + 1] = SUM[pc] >> (16 + p.shift);
+                            Y[2 * pc] = (SUM[pc] & 0xffffu) >> p.shift;
+                        }
+                    }
+                }
+            } else if (emit) {
+#pragma unroll
+                for (int c = 0; c < 12; ++c) {
+                    uint32_t acc = 0u;
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) {
+                        const uint32_t wq = W[((s + 1 + k) % NP) * 12 + c];
+                        acc = half ? ct_dp2<true>(wq, p.ut[k], acc) : ct_dp2<false>(wq, p.ut[k], acc);
+                    }
+                    if (DIV == 0) Y[c] = acc >> p.shift;
+                    else if (DIV == 1) Y[c] = __umulhi(acc, p.magic);
+                    else Y[c] = OUT_U8 ? acc : acc >> (8 * YB);
+                }
+            }
+            if (emit) {
+                uint8_t *grow = orow + (size_t)half * opitch;
+                const bool live = half == 0 || two;
+                if (OUT_U8) {
+                    constexpr uint32_t SEL = 0x0040u + 0x11u * YB;
+                    uint32_t o[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        o[k] = prmt(prmt(Y[CT_COL(4 * k)], Y[CT_COL(4 * k + 1)], SEL), prmt(Y[CT_COL(4 * k + 2)], Y[CT_COL(4 * k + 3)], SEL), 0x5410);
+                    if (wide) {
+                        const uint32_t d = stg + half * WROW;
+                        sts32(d, o[0]); sts32(d + 4, o[1]); sts32(d + 8, o[2]);
+                    } else if (lval > 0 && live) {
+                        uint8_t *gp = grow + lane * 12;
+                        if (lval >= 12 && ((uintptr_t)gp & 3) == 0) {
+                            reinterpret_cast<uint32_t *>(gp)[0] = o[0];
+                            reinterpret_cast<uint32_t *>(gp)[1] = o[1];
+                            reinterpret_cast<uint32_t *>(gp)[2] = o[2];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 12; ++j)
+                                if (j < lval) gp[j] = (uint8_t)(o[j >> 2] >> (8 * (j & 3)));
+                        }
+                    }
+                } else {
+                    if (wide) {
+                        const uint32_t d = stg + half * WROW;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            sts128(d + 16 * k, make_uint4(Y[CT_COL(4 * k)], Y[CT_COL(4 * k + 1)], Y[CT_COL(4 * k + 2)], Y[CT_COL(4 * k + 3)]));
+                    } else if (lval > 0 && live) {
+                        uint32_t *gp = reinterpret_cast<uint32_t *>(grow) + lane * 12;
+#pragma unroll
+                        for (int j = 0; j < 12; ++j)
+                            if (j < lval) gp[j] = Y[CT_COL(j)];
+                    }
+                }
+            }
+        }
+#undef CT_COL
+        if (emit) {
+            if (wide) {
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < NPC; ++j) {
+                    const int c = lane + 32 * j;
+                    if (2 * PPR % 32 == 0 || j + 1 < NPC || c < 2 * PPR) {
+                        const int row = c >= PPR;
+                        if (row == 0 || two)
+                            *reinterpret_cast<uint4 *>(orow + (row ? opitch : 0) + (size_t)(c - row * PPR) * 16) = lds128(stg_rd + 512u * j);
+                    }
+                }
+            }
+            orow += 2 * opitch;
+            ro += 2;
+        }
+    };
+    auto block = [&](auto checked_c) __attribute__((always_inline)) {
+        trip(CtInt<0>{}, checked_c);
+        if constexpr (NP > 1) trip(CtInt<1>{}, checked_c);
+        if constexpr (NP > 2) trip(CtInt<2>{}, checked_c);
+        if constexpr (NP > 3) trip(CtInt<3>{}, checked_c);
+        if constexpr (NP > 4) trip(CtInt<4>{}, checked_c);
+        t0 += NP;
+    };
+
+    // block 0 primes the window; blocks whose trips all exist and all emit two rows run unchecked; the rest checked
+    const int tfull = (nout >> 1) + NP - 1;        // trips [NP-1, tfull) emit two rows each
+    block(CtBool<true>{});
+    while (t0 + NP <= tfull) block(CtBool<false>{});
+    while (t0 < ntrips) block(CtBool<true>{});
+}
+
+template <int K>
+cudaError_t launch_conv_tma_k(ConvTmaParams &p, int out_u8, int div, int vbox, int sm_count, cudaStream_t st) {
+    auto go = [&](auto kern) -> cudaError_t {
+        const int ob = out_u8 ? 1 : 4;
+        static int stages_env = -1, band_env = -1, occ_env = -1;
+        if (occ_env < 0) { const char *e = getenv("OMPIMG_CONV_OCC"); occ_env = e ? atoi(e) : 0; }       // tuning: cap the resident CTAs per SM
+        if (stages_env < 0) { const char *e = getenv("OMPIMG_CONV_STAGES"); stages_env = e ? atoi(e) : 0; }
+        if (band_env < 0) { const char *e = getenv("OMPIMG_CONV_BAND"); band_env = e ? atoi(e) : 0; }
+        // ring depth: three two-row stages per warp measured best for every K (deeper rings are slower: tools/conv_sweep2.sh)
+        p.stages = stages_env > 0 ? max(2, min(16, stages_env)) : 3;
+        int smem = CT_WARPS * (p.stages * (int)ct_stage_bytes(K) + 2 * CT_WPX * 3 * ob + 8 * p.stages) + 128;
+        if (occ_env > 0) smem = max(smem, (int)((227 * 1024) / occ_env - 1024) & ~127);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CT_WARPS * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) return cudaErrorInvalidConfiguration;
+        // Band height (even), chosen to waste least: every band re-reads and re-filters K-1 rows ((K-1)/rows extra), and a
+        // launch of T tasks on the resident warp slots runs in ceil(T/slots) waves of which the last is only partly full.
+        const double slots = (double)sm_count * occ * CT_WARPS;
+        int rpb = 2;
+        double best = -1.0;
+        for (int c = 512; c >= 2 * K; c -= 2) {
+            const long long nb = (p.rows + c - 1) / c;
+            const double tasks = (double)nb * p.nstrips;
+            const double waves = tasks / slots, full = waves <= 1.0 ? 1.0 : (double)(long long)(waves + 0.999999);
+            const double eff = waves / full * (double)c / (double)(c + K - 1);
+            if (eff > best * 1.005) { best = eff; rpb = c; }        // ties go to the taller band
+        }
+        if (p.rows < 2 * K) rpb = (p.rows + 1) & ~1;
+        if (band_env > 0) rpb = max(2, band_env + (band_env & 1));
+        p.band_rows = rpb;
+        const long long nbands = (p.rows + rpb - 1) / rpb;
+        p.ntasks = nbands * p.nstrips;
+        const long long ctas = (p.ntasks + CT_WARPS - 1) / CT_WARPS;
+        if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
+        count_launch();
+        kern<<<(unsigned)ctas, CT_WARPS * 32, smem, st>>>(p);
+        return cudaGetLastError();
+    };
+    if (vbox) {
+        if (div == 0) return out_u8 ? go(conv_tma_kernel<K, true, 0, true>) : go(conv_tma_kernel<K, false, 0, true>);
+        if (div == 1) return out_u8 ? go(conv_tma_kernel<K, true, 1, true>) : go(conv_tma_kernel<K, false, 1, true>);
+        return cudaErrorInvalidValue;
+    }
+    switch (div) {
+        case 0: return out_u8 ? go(conv_tma_kernel<K, true, 0, false>) : go(conv_tma_kernel<K, false, 0, false>);
+        case 1: return out_u8 ? go(conv_tma_kernel<K, true, 1, false>) : go(conv_tma_kernel<K, false, 1, false>);
+        case 3: if (out_u8) return go(conv_tma_kernel<K, true, 3, false>); break;
+        case 4: if (out_u8) return go(conv_tma_kernel<K, true, 4, false>); break;
+    }
+    return cudaErrorInvalidValue;
+}
+
+#endif  // OMPIMG_CONV_TMA_IMPL
+
+}  // namespace ompimg

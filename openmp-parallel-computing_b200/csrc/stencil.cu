@@ -6,6 +6,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "tma.h"
 
 namespace ompimg {
 
@@ -448,10 +449,7 @@ __global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? 3 : 2) sobel_tma_kern
 }
 
 // cuTensorMapEncodeTiled comes from the driver through the runtime (the library links the static runtime only)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
+EncodeTiledFn encode_tiled_fn() {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void *f = nullptr;

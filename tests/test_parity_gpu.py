@@ -412,6 +412,48 @@ def test_row_bands_on_distinct_devices_equal_oracle(gpu, O):
             b.close()
 
 
+def _check_band_conv_and_sums(gpu, O, w, h, devices):
+    rgb = O.synth(h * w * 3, 0xB2000004 + len(devices)).reshape(h, w, 3)
+    b = gpu.Bands(w, h, 3, devices)
+    b.upload(rgb)
+    try:
+        sums, _ = b.channel_sums()
+        assert sums == [int(v) for v in rgb.reshape(-1, 3).astype(np.int64).sum(axis=0)], devices
+        # the reference's result from those sums: (avgs_in + 3*sum) / (rows*cols*3), old/parallel_avg_pixel.c:19-23,40
+        assert [(3 * v) // (h * w * 3) for v in sums] == O.avg_pixel_u8(rgb).tolist(), devices
+        for K in (5, 9, 4):
+            bn = np.array([1.0])
+            for _ in range(K - 1):
+                bn = np.convolve(bn, [1, 1])
+            for kern in (np.ones((K, K), np.int64), np.outer(bn, bn).astype(np.int64)):
+                norm = int(kern.sum())
+                b.convolution(kern, norm)
+                b.convolution(kern, norm)                   # the halo rows copied by the first call must not disturb the second
+                want = O.convolution_u8(rgb, kern, norm).astype(np.uint8)
+                assert np.array_equal(b.download_convolution(), want), (w, h, devices, K)
+        b.rgb_to_edge()                                     # the Sobel bands still see their own rows only
+        assert np.array_equal(b.download_edge(), O.rgb_to_edge(rgb))
+    finally:
+        b.close()
+
+
+def test_row_band_convolution_and_channel_sums(gpu, O):
+    """Row-band forms of a6 and a7 (old/parallel_convolution.c:12-23, old/parallel_avg_pixel.c:17-30): K-1 halo rows copied from
+    the next band(s), partial channel sums added on the host -- equal to the oracle on the whole image.  Bands here live on one
+    device (including bands shorter than K-1 rows); the next test puts every band on its own GPU."""
+    for (w, h, ndev) in ((700, 131, 3), (517, 64, 8), (1030, 40, 16), (300, 33, 1)):
+        _check_band_conv_and_sums(gpu, O, w, h, [0] * ndev)
+
+
+def test_row_band_convolution_on_distinct_devices(gpu, O):
+    """the real P2P path: cudaMemcpyPeerAsync of the K-1 rows below a band from the neighbour GPU (skips on a one-GPU box)"""
+    ndev = gpu.lib().ompimg_device_count()
+    if ndev < 2:
+        pytest.skip("needs at least two GPUs")
+    for n in sorted({2, min(ndev, 4), min(ndev, 8)}):
+        _check_band_conv_and_sums(gpu, O, 2100, 515, list(range(n)))
+
+
 @pytest.mark.parametrize("w", [17, 511, 512, 513, 2047, 4096, 4097, 4112, 8191])
 @pytest.mark.parametrize("h", [3, 4, 5, 6, 7, 17, 130, 131, 132, 133, 134, 262, 263, 264])
 def test_sobel_and_fused_tricky_shapes(gpu, O, w, h):
@@ -669,6 +711,47 @@ def test_separable_convolution_device_layouts(gpu, O, K, kind):
 
 
 
+@pytest.mark.parametrize("K", [3, 5, 7, 9])
+@pytest.mark.parametrize("kind", ["box", "gauss", "gauss_half", "pos_oddnorm", "vbox_pow2"])
+def test_tma_convolution_device_layouts(gpu, O, K, kind):
+    """conv_tma.cuh (16-byte aligned base and pitch: tensor-map copies, one warp per band x 128-pixel strip) through the
+    device entry points: widths that end inside a lane / a warp / exactly on a strip, one to several strips, tiny, odd
+    and band-crossing row counts, uint8 and int32 outputs with aligned and unaligned output rows, padding bytes that must
+    survive -- all against the oracle (old/parallel_convolution.c:8-24)."""
+    L = gpu.lib()
+    kern, norm = _sep_kernel(K, kind)
+    taps = np.ascontiguousarray(kern.reshape(-1), np.int32)
+    #        rows cols  in_pad in_off out_pad
+    cases = [(131, 517, 0, 0, 0), (64, 128, 16, 16, 0), (37, 1100, 128, 0, 16), (2, 3, 0, 32, 4), (1, 1, 0, 0, 0), (3, 129, 0, 0, 0),
+             (1063, 384, 48, 0, 0), (75, 2100, 0, 0, 3), (33, 1028, 0, 0, 0), (19, 127, 0, 0, 1), (600, 256, 0, 0, 0)]
+    for (rows, cols, in_pad, in_off, out_pad) in cases:
+        pr, pc = rows + K - 1, cols + K - 1
+        padded = O.synth(pr * pc * 3, 0x7A50 + K + rows).reshape(pr, pc, 3)
+        want = O.convolution_u8(padded, kern, norm)
+        in_row = pc * 3
+        in_pitch = (in_row + 15) // 16 * 16 + in_pad
+        src = gpu.DeviceBuffer(in_off + in_pitch * pr + 64)
+        src.fill(0xEE)
+        assert L.ompimg_copy2d_h2d(src.ptr + in_off, in_pitch, padded.ctypes.data, in_row, in_row, pr, 0) == 0
+        for u8 in (True, False):
+            ob = 1 if u8 else 4
+            out_row = cols * 3 * ob
+            out_pitch = out_row + out_pad * ob
+            dst = gpu.DeviceBuffer(out_pitch * rows + 64)
+            dst.fill(0x5A)
+            fn = L.ompimg_conv_u8_dev if u8 else L.ompimg_conv_i32_dev
+            ck(gpu, fn(src.ptr + in_off, in_pitch, rows, cols, K, taps.ctypes.data, norm, dst.ptr, out_pitch, 0))
+            gpu.sync(0)
+            raw = dst.download(out_pitch * rows).reshape(rows, out_pitch)
+            got = raw[:, :out_row]
+            exp = want.astype(np.uint8).reshape(rows, out_row) if u8 else want.reshape(rows, cols * 3).view(np.uint8).reshape(rows, out_row)
+            assert np.array_equal(got, exp), (K, kind, rows, cols, in_pad, in_off, out_pad, u8)
+            assert (raw[:, out_row:] == 0x5A).all(), "bytes between output rows were written"
+            assert (dst.download(64, offset=out_pitch * rows) == 0x5A).all(), "bytes past the output were written"
+            dst.free()
+        src.free()
+
+
 def test_channel_sums_device_layouts(gpu, O):
     """a7 through the device entry point: dense and pitched rows, aligned and unaligned bases, rows whose byte
     count is not a multiple of 16 or of the 1536-byte tile (old/parallel_avg_pixel.c:17-30 sums)."""
@@ -736,24 +819,33 @@ def test_full_size_batch_properties(gpu, O):
 
 
 def test_full_size_convolution_box_property(gpu, O):
-    """cfg4 (8192x8192 RGB): a box blur of a constant image is the constant, and a 5x5 box on synthetic
-    data matches the oracle on a sampled window (the oracle on the full image takes too long for CI)."""
+    """cfg4 (8192x8192 RGB): box and binomial blurs on synthetic data match the oracle on sampled windows (the oracle on
+    the full image takes too long for CI) -- for the dense (cols+K-1)*3 pitch (conv_sep.cuh) and for 128-byte aligned
+    rows (conv_tma.cuh); the windows sit on band seams, strip seams and the image's last rows / columns."""
     L = gpu.lib()
     rows = cols = 8192
     for K in (5, 9):
         pr, pc = rows + K - 1, cols + K - 1
-        src = gpu.DeviceBuffer(pr * pc * 3)
-        gpu.synth_dev(src, pr * pc * 3, 0xB2000004)
-        out = gpu.DeviceBuffer(rows * cols * 3)
-        taps = np.ones(K * K, np.int32)
-        ck(gpu, L.ompimg_conv_u8_dev(src.ptr, pc * 3, rows, cols, K, taps.ctypes.data, K * K, out.ptr, cols * 3, 0))
-        gpu.sync(0)
-        y0, x0, hh, ww = 4001, 3001, 40, 64
-        win = np.stack([src.download((ww + K - 1) * 3, offset=((y0 + r) * pc + x0) * 3) for r in range(hh + K - 1)]).reshape(hh + K - 1, ww + K - 1, 3)
-        want = O.convolution_u8(win, np.ones((K, K), np.int64), K * K).astype(np.uint8)
-        got = np.stack([out.download(ww * 3, offset=((y0 + r) * cols + x0) * 3) for r in range(hh)]).reshape(hh, ww, 3)
-        assert np.array_equal(got, want)
-        src.free(); out.free()
+        b = np.array([1.0])
+        for _ in range(K - 1):
+            b = np.convolve(b, [1, 1])
+        gauss = np.outer(b, b).astype(np.int64)
+        for pitch in (pc * 3, (pc * 3 + 127) // 128 * 128):
+            src = gpu.DeviceBuffer(pr * pitch)
+            gpu.synth_dev(src, pr * pitch, 0xB2000004)
+            out = gpu.DeviceBuffer(rows * cols * 3)
+            for kern in (np.ones((K, K), np.int64), gauss):
+                norm = int(kern.sum())
+                taps = np.ascontiguousarray(kern.reshape(-1), np.int32)
+                out.fill(0)
+                ck(gpu, L.ompimg_conv_u8_dev(src.ptr, pitch, rows, cols, K, taps.ctypes.data, norm, out.ptr, cols * 3, 0))
+                gpu.sync(0)
+                for (y0, x0, hh, ww) in ((4001, 3001, 40, 64), (0, 0, 24, 300), (rows - 30, cols - 200, 30, 200), (150, 8192 - 131, 400, 131)):
+                    win = np.stack([src.download((ww + K - 1) * 3, offset=(y0 + r) * pitch + x0 * 3) for r in range(hh + K - 1)]).reshape(hh + K - 1, ww + K - 1, 3)
+                    want = O.convolution_u8(win, kern, norm).astype(np.uint8)
+                    got = np.stack([out.download(ww * 3, offset=((y0 + r) * cols + x0) * 3) for r in range(hh)]).reshape(hh, ww, 3)
+                    assert np.array_equal(got, want), (K, pitch, y0, x0)
+            src.free(); out.free()
 
 
 # ------------------------------------------------------------------------------------------------ drop-in CLI

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--rows", type=int, default=8192, help="rows of the square-ish cfg4 image (sums)")
+    ap.add_argument("--pitch-align", type=int, default=128, help="conv*: input pitch rounded up to this many bytes (1 = the dense (cols+K-1)*3 pitch)")
     ap.add_argument("--natural", action="store_true", help="fused/sobel: frames tiled from the reference's photo instead of uniform noise")
     a = ap.parse_args()
     pkg = importlib.import_module("openmp-parallel-computing_b200")
@@ -74,7 +75,8 @@ def main():
         rows = cols = 8192
         n, px = 1, rows * cols
         pr, pc = rows + K - 1, cols + K - 1
-        src, dst = pkg.DeviceBuffer(pr * pc * 3), pkg.DeviceBuffer(rows * cols * 3)
+        ip = -(-pc * 3 // a.pitch_align) * a.pitch_align
+        src, dst = pkg.DeviceBuffer(pr * ip), pkg.DeviceBuffer(rows * cols * 3)
         pkg.synth_dev(src, src.nbytes, 4)
         taps = np.ones(K * K, np.int32)
         if a.kernel.endswith("g"):                      # binomial taps
@@ -83,7 +85,7 @@ def main():
                 b = np.convolve(b, [1, 1])
             taps = np.ascontiguousarray(np.outer(b, b).reshape(-1), np.int32)
         norm = int(taps.sum())
-        fn = lambda: L.ompimg_conv_u8_dev(src.ptr, pc * 3, rows, cols, K, taps.ctypes.data, norm, dst.ptr, cols * 3, 0)
+        fn = lambda: L.ompimg_conv_u8_dev(src.ptr, ip, rows, cols, K, taps.ctypes.data, norm, dst.ptr, cols * 3, 0)
         bpp = 6
     elif a.kernel == "sums":
         rows, cols = a.rows, 8192
