@@ -607,7 +607,7 @@ def run_ours(args, dist: Dist):
     peak, peak_src = measured_peak()
     kernel_ms = ms / args.steps                               # this rank's launches: one per step
     achieved = BYTES_PER_PX * nf * PX / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "sobel_warp_kernel<3,0> (fused RGB->luma->Sobel, warp-autonomous TMA rings)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "sobel_tma_kernel<3,0,0,0> (fused RGB->luma->Sobel; one warp per band x 512-pixel strip, 3-D tensor-map copies)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic(nf),
                 "algorithmic_bytes_per_launch": BYTES_PER_PX * nf * PX, "frac_of_nominal_8TBs": achieved / 8000.0,
                 "launch": f"rank 0's launch: {nf} frames"}
