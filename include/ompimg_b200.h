@@ -151,7 +151,10 @@ OMPIMG_API int ompimg_rgb_to_edge_batch_host(const uint8_t *rgb, size_t rgb_stri
  * uint8 form: it stores (uint8_t)value, i.e. the low 8 bits of the exact int32 result -- what a C caller gets by
  * narrowing the reference's `long`.  Box/Gaussian taps with norm = sum(taps) never leave 0..255; for taps that can
  * (negative taps, sum(taps) > norm) use ompimg_conv_i32_dev unless that wrap is what you want.  K odd or even, 1..15.
- * in_pitch >= (cols+K-1)*3 and out_pitch >= cols*3 elements of the output type, else OMPIMG_ERR_ARG. */
+ * in_pitch >= (cols+K-1)*3 and out_pitch >= cols*3 elements of the output type, else OMPIMG_ERR_ARG.
+ * Layout: every input row, the last one included, must be readable over its whole pitch (a pitched allocation is rows x pitch).
+ * Rank-1 taps (box, binomial, Gaussian; K 3/5/7/9) on a 16-byte aligned base and pitch take the tensor-map kernel (fastest); the
+ * reference's dense (cols+K-1)*3 pitch takes a kernel that needs 4-byte alignment only; anything else a generic kernel. */
 OMPIMG_API int ompimg_conv_i32_dev(const uint8_t *in, size_t in_pitch, int rows, int cols, int K,
                         const int32_t *taps_host, int32_t norm, int32_t *out, size_t out_pitch, int stream);
 OMPIMG_API int ompimg_conv_u8_dev(const uint8_t *in, size_t in_pitch, int rows, int cols, int K,

@@ -18,17 +18,13 @@
 // outputs) and the last trips of the band run a "checked" body; every block in between runs a body with
 // no per-trip tests (emit, second-row-valid, trip-exists).
 //
-// Arithmetic per lane (4 pixels = 12 output bytes) and input row: identical to conv_sep.cuh --
-//   1. de-interleave: 2 PRMT per planar word;
-//   2. horizontal pass: ceil((K+3)/4) IDP.4A per value against host-shifted tap words;
-//   3. vertical pass: general u: IDP.2A over u16 row pairs in a register ring; constant u (box blur):
-//      running window sums of u16 column pairs, one IADD3 per pair and row;
-//   4. division: shift | multiply-high | byte select (norm 256 / 65536).
+// Arithmetic per lane (4 pixels = 12 output bytes) and input row: conv_lane.cuh (shared with conv_sep.cuh).
 // Instruction budget and the pipe that bounds each K: DESIGN.md 4.3.
 #pragma once
 #include <cuda.h>
 
 #include "common.cuh"
+#include "conv_lane.cuh"
 #include "kernels.h"
 
 namespace ompimg {
@@ -40,8 +36,8 @@ namespace ompimg {
 #define CT_MINB_HI 4                     // ... and the K >= 7 kernels
 #endif
 constexpr int CT_WARPS = 4;              // warps (tasks) per CTA
-constexpr int CT_LPX = 4;                // output pixels per lane
-constexpr int CT_WPX = 32 * CT_LPX;      // output pixels per warp and row
+constexpr int CT_LPX = CL_LPX;           // output pixels per lane
+constexpr int CT_WPX = CL_WPX;           // output pixels per warp and row
 
 constexpr uint32_t ct_box_bytes(int K) { return (uint32_t)(((CT_WPX + K - 1) * 3 + 15) & ~15); }
 constexpr uint32_t ct_stage_bytes(int K) { return (2 * ct_box_bytes(K) + 127u) & ~127u; }
@@ -60,6 +56,7 @@ struct ConvTmaParams {
     uint32_t ut[5];              // vertical tap-pair words: bytes (u[2q], u[2q+1], u[2q-1], u[2q])
     uint32_t magic;
     int32_t shift;
+    int32_t norm;                // unused here (signed taps take conv_sep.cuh); read by the shared lane code's DIV 2 branch only
 };
 
 // band geometry is chosen by the launcher from the kernel's occupancy (conv_tma.cu passes everything else)
@@ -77,33 +74,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
-template <bool HI>
-__device__ __forceinline__ uint32_t ct_dp2(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t d;
-    if (HI) asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    else asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ uint32_t ct_dp4(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t d;
-    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-
-template <int N> struct CtInt { static constexpr int value = N; };
 template <bool B> struct CtBool { static constexpr bool value = B; };
 
 // DIV: 0 acc >> shift | 1 umulhi(acc, magic) | 3 byte 1 (norm 256, u8 out) | 4 byte 2 (norm 65536, u8 out); taps >= 0.
 // VBOX (DIV 0 or 1 only): constant vertical taps, running window sums.
 template <int K, bool OUT_U8, int DIV, bool VBOX>
 __global__ void __launch_bounds__(CT_WARPS * 32, K <= 5 ? CT_MINB_LO : (VBOX ? CT_MINB_HI : CT_MINB_HI + 1)) conv_tma_kernel(const __grid_constant__ ConvTmaParams p) {
-    constexpr int NP = (K + 1) / 2;                 // trips per block; pair-rows in the vertical window
-    constexpr int NPX = CT_LPX + K - 1;             // input pixels per lane
-    constexpr int NWRD = (NPX * 3 + 3) / 4;         // 32-bit words that hold them
-    constexpr int NG = (NPX + 3) / 4;               // planar words per channel
-    constexpr int OB = OUT_U8 ? 1 : 4;
-    constexpr uint32_t WROW = CT_WPX * 3 * OB;      // staging bytes per output row
-    constexpr int RING = VBOX ? (K + 1) * 6 : NP * 12;
+    using Lane = ConvLane<K, OUT_U8, DIV, VBOX>;
+    constexpr int NP = Lane::NP;                    // trips per block; pair-rows in the vertical window
+    constexpr int NWRD = Lane::NWRD;                // 32-bit words that hold a lane's 4+K-1 input pixels
+    constexpr int OB = Lane::OB;
+    constexpr uint32_t WROW = Lane::WROW;           // staging bytes per output row
     constexpr uint32_t BOXB = ct_box_bytes(K), STAGE = ct_stage_bytes(K);
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31;
@@ -145,21 +126,14 @@ __global__ void __launch_bounds__(CT_WARPS * 32, K <= 5 ? CT_MINB_LO : (VBOX ? C
     const int lval = nval - lane * 12;                                          // valid output values of the lane (<= 0: none)
     const uint32_t my = keep(ring0 + (uint32_t)lane * (CT_LPX * 3u));
     const uint32_t ring_bytes = (uint32_t)S * STAGE;
-    // staging: two output rows per warp; written as 12 values per lane, read back as 16-byte pieces
-    // (piece c = lane + 32*j lies in row c / PPR at byte (c % PPR) * 16; j < NPC)
-    constexpr int PPR = (int)WROW / 16, NPC = 2 * PPR / 32 + (2 * PPR % 32 ? 1 : 0);
     const uint32_t stg = staging0 + (uint32_t)lane * (12u * OB);
     const uint32_t stg_rd = staging0 + (uint32_t)lane * 16u;
     const size_t opitch = p.out_pitch;
     uint8_t *orow = p.out + (size_t)ya * opitch + (size_t)seg0 * OB;            // next output row of this warp
     int ro = ya;
 
-    uint32_t W[RING];            // VBOX: P[slot][6] (slot = input row mod K+1); else W[pair-row slot][12]
-#pragma unroll
-    for (int q = 0; q < RING; ++q) W[q] = 0u;
-    uint32_t SUM[6];             // VBOX: running window sums, two columns per register
-#pragma unroll
-    for (int q = 0; q < 6; ++q) SUM[q] = 0u;
+    Lane L;                      // the vertical window (register ring / running sums) of this lane's 12 output columns
+    L.init();
 
     uint32_t so = 0, fb = bar0, ph = 0;            // ring position (stage offset, its barrier, its phase) of the next trip
     int t0 = 0;                                    // trip number of the current block's first trip
@@ -178,6 +152,10 @@ __global__ void __launch_bounds__(CT_WARPS * 32, K <= 5 ? CT_MINB_LO : (VBOX ? C
 #pragma unroll
             for (int i = 0; i < NWRD; ++i) w[rho][i] = lds32(a + 4 * i);
         }
+        // The refill below is an async-proxy WRITE of the stage these generic-proxy loads READ: the proxy fence orders each
+        // lane's loads before it, the warp barrier collects the lanes.  Without it the copy (an L2 hit on small images) can land
+        // before loads that still wait in the LSU queue behind this lane's output stores (seen with int32 per-lane stores).
+        fence_async_smem();
         __syncwarp();                                  // every lane holds both rows (and has read the previous trip's staging rows)
         if (ct_elect() && t + S < ntrips) request(so, fb, t + S);
         so += STAGE; fb += 8;
@@ -185,150 +163,18 @@ __global__ void __launch_bounds__(CT_WARPS * 32, K <= 5 ? CT_MINB_LO : (VBOX ? C
 
         const bool emit = !CHECKED || t >= NP - 1;
         const bool two = !CHECKED || ro + 1 < yb;
-        uint32_t h[2][12];
-#pragma unroll
-        for (int rho = 0; rho < 2; ++rho) {
-            // planar words: X[ch][m] = channel ch of pixels 4m .. 4m+3 (pixels past NPX meet zero taps)
-            uint32_t X[3][NG];
-#pragma unroll
-            for (int m = 0; m < NG; ++m) {
-                const uint32_t wa = w[rho][3 * m];
-                const uint32_t wb = 3 * m + 1 < NWRD ? w[rho][3 * m + 1] : 0u;
-                X[0][m] = prmt(wa, wb, 0x0630);     // r0 r1 r2 .
-                X[1][m] = prmt(wa, wb, 0x0741);     // g0 g1 g2 .
-                X[2][m] = prmt(wa, wb, 0x0052);     // b0 b1 . .
-                if (3 * m + 2 < NWRD) {
-                    const uint32_t wc = w[rho][3 * m + 2];
-                    X[0][m] = prmt(X[0][m], wc, 0x5210);   // r3 = wc.b1
-                    X[1][m] = prmt(X[1][m], wc, 0x6210);   // g3 = wc.b2
-                    X[2][m] = prmt(X[2][m], wc, 0x7410);   // b2 = wc.b0, b3 = wc.b3
-                }
-            }
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint32_t acc = 0u;
-#pragma unroll
-                    for (int m = 0; m < NG; ++m)
-                        if (4 * m + 3 - i >= 0 && 4 * m - i < K) acc = ct_dp4(X[ch][m], p.th[i][m < 3 ? m : 0], acc);
-                    h[rho][ch * 4 + i] = acc;
-                }
-        }
-        if (!VBOX) {
-#pragma unroll
-            for (int c = 0; c < 12; ++c) W[s * 12 + c] = prmt(h[0][c], h[1][c], 0x5410);
-        }
-
-        // value j of the lane (byte column 12*lane + j) is pixel j/3, channel j%3: column index (j%3)*4 + j/3
-#define CT_COL(j) (((j) % 3) * 4 + (j) / 3)
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            // Y[c]: the quotient of column c, in byte YB of the register (u8 output) or shifted down (int32 output)
-            uint32_t Y[12];
-            constexpr int YB = VBOX ? (DIV == 1 ? 2 : 0) : DIV == 3 ? 1 : DIV == 4 ? 2 : 0;
-            if (VBOX) {
-                // window sums of the K newest rows: S += P[row] - P[row-K], two columns per IADD3
-                constexpr int R = K + 1;
-                constexpr int slot_base = 2 * s;
-                const int slot = slot_base + half, old = (slot_base + half + 1) % R;
-#pragma unroll
-                for (int pc = 0; pc < 6; ++pc) {
-                    const uint32_t pn = prmt(h[half][2 * pc], h[half][2 * pc + 1], 0x5410);
-                    SUM[pc] = SUM[pc] + pn - W[old * 6 + pc];
-                    W[slot * 6 + pc] = pn;
-                }
-                if (emit) {
-#pragma unroll
-                    for (int pc = 0; pc < 6; ++pc) {
-                        if (DIV == 1) {
-                            // floor(s/norm) sits in bits 16.. of umulhi(s << 16 | anything below, magic) (host-checked range)
-                            Y[2 * pc + 1] = __umulhi(SUM[pc], p.magic);
-                            Y[2 * pc] = __umulhi(SUM[pc] << 16, p.magic);
-                            if (!OUT_U8) { Y[2 * pc + 1] >>= 16; Y[2 * pc] >>= 16; }
-                        } else {
-                            Y[2 * pc + 1] = SUM[pc] >> (16 + p.shift);
-                            Y[2 * pc] = (SUM[pc] & 0xffffu) >> p.shift;
-                        }
-                    }
-                }
-            } else if (emit) {
-#pragma unroll
-                for (int c = 0; c < 12; ++c) {
-                    uint32_t acc = 0u;
-#pragma unroll
-                    for (int k = 0; k < NP; ++k) {
-                        const uint32_t wq = W[((s + 1 + k) % NP) * 12 + c];
-                        acc = half ? ct_dp2<true>(wq, p.ut[k], acc) : ct_dp2<false>(wq, p.ut[k], acc);
-                    }
-                    if (DIV == 0) Y[c] = acc >> p.shift;
-                    else if (DIV == 1) Y[c] = __umulhi(acc, p.magic);
-                    else Y[c] = OUT_U8 ? acc : acc >> (8 * YB);
-                }
-            }
-            if (emit) {
-                uint8_t *grow = orow + (size_t)half * opitch;
-                const bool live = half == 0 || two;
-                if (OUT_U8) {
-                    constexpr uint32_t SEL = 0x0040u + 0x11u * YB;
-                    uint32_t o[3];
-#pragma unroll
-                    for (int k = 0; k < 3; ++k)
-                        o[k] = prmt(prmt(Y[CT_COL(4 * k)], Y[CT_COL(4 * k + 1)], SEL), prmt(Y[CT_COL(4 * k + 2)], Y[CT_COL(4 * k + 3)], SEL), 0x5410);
-                    if (wide) {
-                        const uint32_t d = stg + half * WROW;
-                        sts32(d, o[0]); sts32(d + 4, o[1]); sts32(d + 8, o[2]);
-                    } else if (lval > 0 && live) {
-                        uint8_t *gp = grow + lane * 12;
-                        if (lval >= 12 && ((uintptr_t)gp & 3) == 0) {
-                            reinterpret_cast<uint32_t *>(gp)[0] = o[0];
-                            reinterpret_cast<uint32_t *>(gp)[1] = o[1];
-                            reinterpret_cast<uint32_t *>(gp)[2] = o[2];
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 12; ++j)
-                                if (j < lval) gp[j] = (uint8_t)(o[j >> 2] >> (8 * (j & 3)));
-                        }
-                    }
-                } else {
-                    if (wide) {
-                        const uint32_t d = stg + half * WROW;
-#pragma unroll
-                        for (int k = 0; k < 3; ++k)
-                            sts128(d + 16 * k, make_uint4(Y[CT_COL(4 * k)], Y[CT_COL(4 * k + 1)], Y[CT_COL(4 * k + 2)], Y[CT_COL(4 * k + 3)]));
-                    } else if (lval > 0 && live) {
-                        uint32_t *gp = reinterpret_cast<uint32_t *>(grow) + lane * 12;
-#pragma unroll
-                        for (int j = 0; j < 12; ++j)
-                            if (j < lval) gp[j] = Y[CT_COL(j)];
-                    }
-                }
-            }
-        }
-#undef CT_COL
+        L.template rows2<s>(w, p, emit, two, wide, lval, lane, stg, stg_rd, orow, opitch);
         if (emit) {
-            if (wide) {
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < NPC; ++j) {
-                    const int c = lane + 32 * j;
-                    if (2 * PPR % 32 == 0 || j + 1 < NPC || c < 2 * PPR) {
-                        const int row = c >= PPR;
-                        if (row == 0 || two)
-                            *reinterpret_cast<uint4 *>(orow + (row ? opitch : 0) + (size_t)(c - row * PPR) * 16) = lds128(stg_rd + 512u * j);
-                    }
-                }
-            }
             orow += 2 * opitch;
             ro += 2;
         }
     };
     auto block = [&](auto checked_c) __attribute__((always_inline)) {
-        trip(CtInt<0>{}, checked_c);
-        if constexpr (NP > 1) trip(CtInt<1>{}, checked_c);
-        if constexpr (NP > 2) trip(CtInt<2>{}, checked_c);
-        if constexpr (NP > 3) trip(CtInt<3>{}, checked_c);
-        if constexpr (NP > 4) trip(CtInt<4>{}, checked_c);
+        trip(ClInt<0>{}, checked_c);
+        if constexpr (NP > 1) trip(ClInt<1>{}, checked_c);
+        if constexpr (NP > 2) trip(ClInt<2>{}, checked_c);
+        if constexpr (NP > 3) trip(ClInt<3>{}, checked_c);
+        if constexpr (NP > 4) trip(ClInt<4>{}, checked_c);
         t0 += NP;
     };
 

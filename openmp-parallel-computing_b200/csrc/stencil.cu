@@ -382,6 +382,9 @@ __global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? 3 : 2) sobel_tma_kern
         load_row<CH>(addr, ec.edge_off, raw);
         if (RGBOUT) raw.e0 = lds32(sbox0 + (uint32_t)s * 128u + (uint32_t)RHO * 32u + side_off);      // the halo blocks of the stage may be overwritten already
         if (RHO == 2) {
+            // the refill is an async-proxy WRITE of the stage the generic-proxy loads above READ: the proxy fence orders each
+            // lane's loads before it, the warp barrier collects the lanes (conv_tma.cuh has the failure this prevents)
+            fence_async_smem();
             __syncwarp();                                   // every lane holds the stage's three rows
             if (elect_one_sync() && t + S < ntrips) request(s, t + S);
         }

@@ -752,6 +752,31 @@ def test_tma_convolution_device_layouts(gpu, O, K, kind):
         src.free()
 
 
+def test_tma_convolution_refill_race_stress(gpu, O):
+    """Regression: the warp-autonomous kernels refill a ring stage (an async-proxy write) right after reading it.  On an
+    L2-resident image with int32 per-lane output stores (unaligned output rows: the LSU queue fills with stores) the copy used
+    to land before queued loads of the same stage had read it -- about two runs in three gave a few wrong values in a band's
+    last rows.  Fixed by a proxy fence before the refill (conv_tma.cuh, stencil.cu); repeated here so that a regression shows."""
+    L = gpu.lib()
+    K, rows, cols = 9, 75, 2100
+    kern, norm = _sep_kernel(K, "pos_oddnorm")
+    taps = np.ascontiguousarray(kern.reshape(-1), np.int32)
+    pr, pc = rows + K - 1, cols + K - 1
+    padded = O.synth(pr * pc * 3, 0x7A50 + K + rows).reshape(pr, pc, 3)
+    want = O.convolution_u8(padded, kern, norm).reshape(rows, cols * 3).astype(np.int32)
+    in_pitch = (pc * 3 + 15) // 16 * 16
+    src = to_dev_pitched(gpu, padded.reshape(pr, pc * 3), in_pitch)
+    out_pitch = (cols * 3 + 3) * 4
+    dst = gpu.DeviceBuffer(out_pitch * rows + 64)
+    for rep in range(40):
+        dst.fill(0x5A)
+        ck(gpu, L.ompimg_conv_i32_dev(src.ptr, in_pitch, rows, cols, K, taps.ctypes.data, norm, dst.ptr, out_pitch, 0))
+        gpu.sync(0)
+        got = dst.download(out_pitch * rows).reshape(rows, out_pitch)[:, :cols * 12].copy().view(np.int32)
+        assert np.array_equal(got, want), rep
+    src.free(); dst.free()
+
+
 def test_channel_sums_device_layouts(gpu, O):
     """a7 through the device entry point: dense and pitched rows, aligned and unaligned bases, rows whose byte
     count is not a multiple of 16 or of the 1536-byte tile (old/parallel_avg_pixel.c:17-30 sums)."""
