@@ -563,6 +563,45 @@ def bands_single_process_leg(args, dist, pkg, peak):
     return rec
 
 
+def bands_old_kernels_leg(args, dist, pkg, peak):
+    """row-band forms of the old/ kernels on the cfg5 image (old/parallel_convolution.c:12-23 as a 5x5 box blur with the image as the
+    pre-padded input: K-1 halo rows per band by P2P copies; old/parallel_avg_pixel.c:17-30: per-GPU partial channel sums added on
+    the host).  One process (rank 0) drives all N GPUs; results are checked against constants derived from the CPU oracle
+    (tools/make_bands_checksum.py --extras -> tests/golden/bands_cfg5.json)."""
+    rec = None
+    if dist.rank == 0:
+        try:
+            gold = {}
+            gp = ROOT / "tests" / "golden" / "bands_cfg5.json"
+            if gp.exists() and args.bands_size == BANDS_W:
+                gold = json.loads(gp.read_text())
+            n = args.bands_size
+            b = pkg.Bands(n, n, 3, list(range(dist.world)))
+            b.synth(BANDS_SEED)
+            sums, _ = b.channel_sums()
+            ms_s = sorted(b.channel_sums()[1] for _ in range(5))
+            K = 5
+            kern = np.ones((K, K), np.int32)
+            for _ in range(2):
+                b.convolution(kern, K * K)
+            ms_c = sorted(b.convolution(kern, K * K) for _ in range(max(5, args.bands_steps // 2)))
+            csum = b.convolution_checksum()
+            opx = (n - K + 1) ** 2
+            rec = {"devices": dist.world,
+                   "channel_sums": {"ms_median": ms_s[len(ms_s) // 2], "gpixel_s": n * n / ms_s[len(ms_s) // 2] / 1e6, "sums": sums,
+                                    "equals_oracle": (sums == gold["channel_sums"]) if "channel_sums" in gold else None},
+                   "conv_box5x5": {"ms_median": ms_c[len(ms_c) // 2], "ms_best": ms_c[0], "gpixel_s": opx / ms_c[len(ms_c) // 2] / 1e6,
+                                   "frac_of_measured_peak_per_gpu": 6 * opx / (ms_c[len(ms_c) // 2] * 1e-3) / 1e9 / dist.world / peak,
+                                   "halo": "4 rows below each band, cudaMemcpyPeerAsync from the next GPU on the band's stream (inside the timed region)",
+                                   "checksum": csum, "equals_oracle": (csum == gold["conv5_box_sum"]) if "conv5_box_sum" in gold else None},
+                   "timing": "per-device CUDA events around each band's copies + launch, max over devices, median of the steps"}
+            b.close()
+        except Exception as e:
+            rec = {"error": repr(e)[:300]}
+    dist.host_barrier()
+    return rec
+
+
 def run_ours(args, dist: Dist):
     pkg = importlib.import_module("openmp-parallel-computing_b200")
     numa = bind_to_gpu_numa_node(dist.local) if dist.world > 1 and not os.environ.get("OMPIMG_NO_NUMA") else None
@@ -623,6 +662,10 @@ def run_ours(args, dist: Dist):
             sp = bands_single_process_leg(args, dist, pkg, peak)
             if bands is not None:
                 bands["single_process"] = sp
+        if not args.no_bands_single:
+            ok = bands_old_kernels_leg(args, dist, pkg, peak)
+            if bands is not None:
+                bands["old_kernels"] = ok
 
     cpu = None
     if dist.rank == 0 and dist.world == 1 and not args.no_cpu:

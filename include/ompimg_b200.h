@@ -214,6 +214,7 @@ OMPIMG_API int  ompimg_bands_checksum(ompimg_bands *b, unsigned long long *sum);
  * copied from the next device(s) over NVLink (cudaMemcpyPeerAsync) before the band's kernel starts: one exchange step. */
 OMPIMG_API int  ompimg_bands_conv_u8(ompimg_bands *b, int K, const int32_t *taps, int32_t norm, float *ms_max);
 OMPIMG_API int  ompimg_bands_download_conv(ompimg_bands *b, uint8_t *out_host);     /* dense (height-K+1) x (width-K+1) x 3 */
+OMPIMG_API int  ompimg_bands_conv_checksum(ompimg_bands *b, unsigned long long *sum);   /* sum of all output bytes */
 /* a7 over bands (old/parallel_avg_pixel.c:17-30): per-device partial channel sums, added on the host */
 OMPIMG_API int  ompimg_bands_channel_sums(ompimg_bands *b, unsigned long long *sums3, float *ms_max);
 

@@ -116,6 +116,7 @@ _SIGS = {
     "ompimg_bands_checksum": (C.c_int, [_vp, C.POINTER(C.c_ulonglong)]),
     "ompimg_bands_conv_u8": (C.c_int, [_vp, C.c_int, _vp, C.c_int32, C.POINTER(C.c_float)]),
     "ompimg_bands_download_conv": (C.c_int, [_vp, _vp]),
+    "ompimg_bands_conv_checksum": (C.c_int, [_vp, C.POINTER(C.c_ulonglong)]),
     "ompimg_bands_channel_sums": (C.c_int, [_vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_float)]),
     "ompimg_jpeg_probe": (C.c_int, [_vp, _sz, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ompimg_jpeg_parse": (_vp, [_vp, _sz]),
@@ -495,6 +496,11 @@ class Bands:
         out = np.zeros((self.h - self.k_ + 1, self.w - self.k_ + 1, 3), np.uint8)
         _ck(lib().ompimg_bands_download_conv(self.h_, _ptr(out)), "bands_download_conv")
         return out
+
+    def convolution_checksum(self) -> int:
+        s = C.c_ulonglong()
+        _ck(lib().ompimg_bands_conv_checksum(self.h_, C.byref(s)), "bands_conv_checksum")
+        return int(s.value)
 
     def channel_sums(self):
         """a7 over the bands (old/parallel_avg_pixel.c:17-30): per-device partial sums added on the host; (sums[3], device ms)"""

@@ -358,6 +358,33 @@ extern "C" int ompimg_bands_download_conv(ompimg_bands *b, uint8_t *out_host) {
     return bands_sync(b);
 }
 
+// sum of all bytes of the banded convolution output (the known-answer check of a full-size run)
+extern "C" int ompimg_bands_conv_checksum(ompimg_bands *b, unsigned long long *sum) {
+    if (!b || !sum || !b->conv[0]) return OMPIMG_ERR_ARG;
+    const int K = b->conv_k, out_h = b->h - K + 1, row = (b->w - K + 1) * 3;
+    unsigned long long total = 0;
+    for (int i = 0; i < b->ndev; ++i) {
+        BCK(cudaSetDevice(b->dev[i]));
+        const int y0 = b->row0[i], y1 = b->row0[i + 1] < out_h ? b->row0[i + 1] : out_h;
+        BCK(cudaMemsetAsync(b->sum[i], 0, 8, b->st[i]));
+        if (y1 > y0) {
+            count_launch();
+            byte_sum_kernel<<<b->sm_count[i] * 8, 256, 0, b->st[i]>>>(b->conv[i], b->cpitch, 0, row, 0, y1 - y0, b->sum[i]);
+            BCK(cudaGetLastError());
+        }
+    }
+    for (int i = 0; i < b->ndev; ++i) {
+        BCK(cudaSetDevice(b->dev[i]));
+        unsigned long long s = 0;
+        BCK(cudaMemcpyAsync(&s, b->sum[i], 8, cudaMemcpyDeviceToHost, b->st[i]));
+        BCK(cudaStreamSynchronize(b->st[i]));
+        total += s;
+    }
+    BCK(cudaSetDevice(b->home));
+    *sum = total;
+    return OMPIMG_OK;
+}
+
 // a7 (old/parallel_avg_pixel.c:17-30) over bands: every device sums its band (partial sums), the host adds the ndev triples --
 // 24 bytes per device, the reduction the reference does with its `reduction(+:avgs)` clause.
 extern "C" int ompimg_bands_channel_sums(ompimg_bands *b, unsigned long long *sums3, float *ms_max) {

@@ -431,6 +431,7 @@ def _check_band_conv_and_sums(gpu, O, w, h, devices):
                 b.convolution(kern, norm)                   # the halo rows copied by the first call must not disturb the second
                 want = O.convolution_u8(rgb, kern, norm).astype(np.uint8)
                 assert np.array_equal(b.download_convolution(), want), (w, h, devices, K)
+                assert b.convolution_checksum() == int(want.astype(np.int64).sum())
         b.rgb_to_edge()                                     # the Sobel bands still see their own rows only
         assert np.array_equal(b.download_edge(), O.rgb_to_edge(rgb))
     finally:
