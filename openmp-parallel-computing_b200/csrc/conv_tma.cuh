@@ -203,17 +203,22 @@ cudaError_t launch_conv_tma_k(ConvTmaParams &p, int out_u8, int div, int vbox, i
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CT_WARPS * 32, smem);
         if (e != cudaSuccess) return e;
         if (occ < 1) return cudaErrorInvalidConfiguration;
-        // Band height (even), chosen to waste least: every band re-reads and re-filters K-1 rows ((K-1)/rows extra), and a
-        // launch of T tasks on the resident warp slots runs in ceil(T/slots) waves of which the last is only partly full.
-        const double slots = (double)sm_count * occ * CT_WARPS;
+        // Band height (even).  A launch of T = bands x strips tasks runs in F = ceil(T / slots) waves on the resident warp slots.  With
+        // one wave the launch lasts as long as its tallest band plus the K-1 priming rows every band re-reads and re-filters; with
+        // many waves early finishers pick up new tasks and only the total work W (rows + K-1 summed over the tasks) counts.  Estimate
+        // W/slots + (F*(c+K-1) - W/slots)/F, exact at F = 1 and -> W/slots for large F, and take the height that minimises it (ties:
+        // the taller band).
+        // K >= 7: tasks for four CTAs per SM measured best even where five fit (the IDP pipe is saturated by 16 warps; a fifth CTA
+        // splits the same throughput and adds a band's worth of re-filtered rows): 9x9 binomial 474 Gpx/s with 5, 503-537 with 4
+        const double slots = (double)sm_count * (K >= 7 ? min(occ, 4) : occ) * CT_WARPS;
         int rpb = 2;
         double best = -1.0;
         for (int c = 512; c >= 2 * K; c -= 2) {
             const long long nb = (p.rows + c - 1) / c;
-            const double tasks = (double)nb * p.nstrips;
-            const double waves = tasks / slots, full = waves <= 1.0 ? 1.0 : (double)(long long)(waves + 0.999999);
-            const double eff = waves / full * (double)c / (double)(c + K - 1);
-            if (eff > best * 1.005) { best = eff; rpb = c; }        // ties go to the taller band
+            const double tasks = (double)nb * p.nstrips, full = (double)(long long)((tasks + slots - 1) / slots);
+            const double work = (double)p.nstrips * ((double)p.rows + (double)(K - 1) * nb) / slots;
+            const double span = work + (full * (c + K - 1) - work) / full;
+            if (best < 0 || span < best * 0.999) { best = span; rpb = c; }
         }
         if (p.rows < 2 * K) rpb = (p.rows + 1) & ~1;
         if (band_env > 0) rpb = max(2, band_env + (band_env & 1));
