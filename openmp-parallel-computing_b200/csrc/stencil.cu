@@ -574,51 +574,55 @@ struct PrepParams {
     uint8_t *entries; size_t entry_pitch;                // out: [frame][row][nstrips+1] x 16 bytes
 };
 // Reads the image only; everything the in-place kernel could find overwritten is copied out first (see sobel_tma_kernel).
+// Three ranges of CTAs, no 64-bit divisions: [0, nA) copy every band's first and last source row (one thread per 16-byte chunk),
+// [nA, nA+nC) build the replicated border rows, the rest write the strip-boundary entries (one thread per entry, two aligned
+// 32-bit loads: the pixel left of boundary k ends at byte 1536k, the pixel right of it starts there).
 __global__ void __launch_bounds__(256) pass_prepare_kernel(const PrepParams p) {
-    const long long chunks = p.row_bytes16 / 16;
-    const long long nA = (long long)p.nframes * p.nbands * 2 * chunks;          // band rows
-    const long long nC = (long long)p.nframes * 2 * chunks;                    // border rows (replicated)
-    const long long nB = (long long)p.nframes * p.h * (p.nstrips + 1);         // strip-boundary entries
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nA + nC + nB; i += (long long)gridDim.x * blockDim.x) {
-        if (i < nA) {
-            const long long c = i % chunks, q = i / chunks;
-            const int which = (int)(q & 1), b = (int)((q >> 1) % p.nbands);
-            const long long f = (q >> 1) / p.nbands;
-            const int a0 = b * p.rpb, yb = min(p.h, (b + 1) * p.rpb + 1), a1 = min(yb, p.h - 1);
-            if (a1 - a0 + 1 < 3) continue;                                      // a band without output rows is never consumed
-            const int r = which ? a1 : a0;
-            const uint4 v = *reinterpret_cast<const uint4 *>(p.img + f * p.stride + (size_t)r * p.pitch + c * 16);
-            *reinterpret_cast<uint4 *>(p.rows + (size_t)q * p.row_pitch + c * 16) = v;
-        } else if (i < nA + nC) {
-            const long long j = i - nA, c = j % chunks, q = j / chunks;          // q = frame*2 + which
-            const int which = (int)(q & 1);
-            const long long f = q >> 1;
-            uint32_t o[4] = {0, 0, 0, 0};
-            if (p.edge) {
-                const uint8_t *er = p.edge + f * p.estride + (size_t)(which ? p.h - 1 : 0) * p.epitch;
+    const uint32_t chunks = p.row_bytes16 / 16;
+    const uint32_t cpr = (chunks + 255u) / 256u;                                // CTAs per copied row
+    const uint32_t nA = (uint32_t)p.nframes * (uint32_t)p.nbands * 2u * cpr, nC = (uint32_t)p.nframes * 2u * cpr;
+    const uint32_t blk = blockIdx.x;
+    if (blk < nA) {
+        const uint32_t q = blk / cpr, c = (blk - q * cpr) * 256u + threadIdx.x;  // q = (frame * nbands + band) * 2 + which
+        if (c >= chunks) return;
+        const uint32_t which = q & 1u, fb = q >> 1, f = fb / (uint32_t)p.nbands, bnd = fb - f * (uint32_t)p.nbands;
+        const int a0 = (int)bnd * p.rpb, yb = min(p.h, ((int)bnd + 1) * p.rpb + 1), a1 = min(yb, p.h - 1);
+        if (a1 - a0 + 1 < 3) return;                                            // a band without output rows is never consumed
+        const int r = which ? a1 : a0;
+        const uint4 v = *reinterpret_cast<const uint4 *>(p.img + (size_t)f * p.stride + (size_t)r * p.pitch + (size_t)c * 16);
+        *reinterpret_cast<uint4 *>(p.rows + (size_t)q * p.row_pitch + (size_t)c * 16) = v;
+    } else if (blk < nA + nC) {
+        const uint32_t j = blk - nA, q = j / cpr, c = (j - q * cpr) * 256u + threadIdx.x;       // q = frame * 2 + which
+        if (c >= chunks) return;
+        const uint32_t which = q & 1u, f = q >> 1;
+        uint32_t o[4] = {0, 0, 0, 0};
+        if (p.edge) {
+            const uint8_t *er = p.edge + (size_t)f * p.estride + (size_t)(which ? p.h - 1 : 0) * p.epitch;
+            const uint32_t lim = (uint32_t)p.w * 3u;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const long long byte = c * 16 + k;
-                    const uint32_t v = byte < (long long)p.w * 3 ? er[byte / 3] : 0u;
-                    o[k >> 2] |= v << (8 * (k & 3));
-                }
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t byte = c * 16u + k;
+                const uint32_t v = byte < lim ? er[byte / 3u] : 0u;
+                o[k >> 2] |= v << (8 * (k & 3));
             }
-            *reinterpret_cast<uint4 *>(p.border + (size_t)q * p.row_pitch + c * 16) = make_uint4(o[0], o[1], o[2], o[3]);
-        } else {
-            const long long j = i - nA - nC;
-            const int k = (int)(j % (p.nstrips + 1));
-            const long long fy = j / (p.nstrips + 1), f = fy / p.h;
-            const int y = (int)(fy - f * p.h);
-            const uint8_t *row = p.img + f * p.stride + (size_t)y * p.pitch;
-            const uint8_t *er = p.edge ? p.edge + f * p.estride + (size_t)y * p.epitch : nullptr;
-            const int xb = k * 512;
-            uint32_t L, R;
-            if (k == 0) { const uint32_t bl = er ? er[0] : 0u; L = bl * 0x010101u; }
-            else { const uint8_t *q = row + (size_t)(xb - 1) * 3; L = q[0] | (q[1] << 8) | (q[2] << 16); }
-            if (xb < p.w) { const uint8_t *q = row + (size_t)xb * 3; R = q[0] | (q[1] << 8) | (q[2] << 16); }
-            else { const uint32_t br = er ? er[p.w - 1] : 0u; R = br * 0x010101u; }
-            *reinterpret_cast<uint4 *>(p.entries + (size_t)fy * p.entry_pitch + (size_t)k * 16) = make_uint4(L, R, 0u, 0u);
         }
+        *reinterpret_cast<uint4 *>(p.border + (size_t)q * p.row_pitch + (size_t)c * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+        const uint32_t ne = (uint32_t)p.nstrips + 1u;
+        const unsigned long long item = (unsigned long long)(blk - nA - nC) * 256u + threadIdx.x;     // (frame * h + y) * ne + k
+        if (item >= (unsigned long long)p.nframes * (unsigned long long)p.h * ne) return;
+        const uint32_t fy = (uint32_t)(item / ne), k = (uint32_t)(item - (unsigned long long)fy * ne);      // nframes * h < 2^32 (checked by the launcher)
+        const uint32_t f = fy / (uint32_t)p.h, y = fy - f * (uint32_t)p.h;
+        const uint8_t *row = p.img + (size_t)f * p.stride + (size_t)y * p.pitch;
+        const uint8_t *er = p.edge ? p.edge + (size_t)f * p.estride + (size_t)y * p.epitch : nullptr;
+        const uint32_t xb = k * 512u;
+        uint32_t L, R;
+        if (k == 0) L = (er ? (uint32_t)er[0] : 0u) * 0x010101u;
+        else if (xb - 1u < (uint32_t)p.w) L = *reinterpret_cast<const uint32_t *>(row + (size_t)xb * 3 - 4) >> 8;      // bytes 1536k-3 .. 1536k-1
+        else L = 0u;                                                            // no pixel there (the last strip is ragged): never looked at
+        if (xb < (uint32_t)p.w) R = *reinterpret_cast<const uint32_t *>(row + (size_t)xb * 3) & 0xffffffu;
+        else R = (er ? (uint32_t)er[p.w - 1] : 0u) * 0x010101u;
+        *reinterpret_cast<uint4 *>(p.entries + (size_t)fy * p.entry_pitch + (size_t)k * 16) = make_uint4(L, R, 0u, 0u);
     }
 }
 
@@ -653,8 +657,10 @@ cudaError_t launch_gray_sobel_pass_inplace(uint8_t *img, size_t pitch, size_t st
     pp.rows = scratch; pp.row_pitch = sz.row_pitch;
     pp.border = scratch + sz.rows_bytes;
     pp.entries = scratch + sz.rows_bytes + sz.border_bytes; pp.entry_pitch = sz.entry_pitch;
-    const long long work = (long long)nframes * ((long long)(d.nbands + 1) * 2 * (sz.row_pitch / 16) + (long long)h * (d.nstrips + 1));
-    const int grid = (int)max(1LL, min((work + 255) / 256, (long long)sm_count * 16));
+    const long long cpr = ((long long)(sz.row_pitch / 16) + 255) / 256;
+    const long long ctas = (long long)nframes * (d.nbands + 1) * 2 * cpr + ((long long)nframes * h * (d.nstrips + 1) + 255) / 256;
+    if (ctas > 0x7fffffffLL || (long long)nframes * h > 0xffffffffLL) return cudaErrorInvalidValue;
+    const int grid = (int)ctas;
     count_launch();
     pass_prepare_kernel<<<grid, 256, 0, st>>>(pp);
     cudaError_t e = cudaGetLastError();
