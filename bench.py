@@ -763,14 +763,18 @@ def other_kernels(pkg, L, peak, with_cpu=True):
     n3 = min(n, s.nbytes // (w3 * h3))
     out[f"sobel_plane_3840x2160x{n3}"] = entry(n3 * w3 * h3, 2, timeit(lambda: L.ompimg_sobel_dev(s.ptr, w3, d.ptr, w3, w3, h3, n3, w3 * h3, w3 * h3, 0)))
     s.free(); d.free()
-    # a5 semantics: RGB in place -> RGB edge (one fused launch), 3840x2160 x 64
-    n5 = 64
+    # a5 semantics: RGB in place -> RGB edge, 3840x2160 x 64, the driver's loop of 10 passes per call (main_with_sobel.c:51-74 x passes):
+    # one preparation kernel per call, then one fused launch per pass (each pass writes the next one's seam data)
+    n5, npass = 64, 10
     img = pkg.DeviceBuffer(n5 * PX * 3); e = pkg.DeviceBuffer(n5 * PX)
     pkg.synth_dev(img, img.nbytes, 3); e.fill(0)
     l0 = pkg.launch_count()
-    sec = timeit(lambda: L.ompimg_gray_sobel_pass_dev(img.ptr, W * 3, 3, e.ptr, W, W, H, n5, PX * 3, PX, 0))
+    sec = timeit(lambda: L.ompimg_gray_sobel_passes_dev(img.ptr, W * 3, 3, e.ptr, W, W, H, n5, PX * 3, PX, npass, 0), 3) / npass
     out["gray_sobel_pass_rgb_inplace_3840x2160x64"] = entry(n5 * PX, 6, sec)
-    out["gray_sobel_pass_rgb_inplace_3840x2160x64"]["launches_per_pass"] = (pkg.launch_count() - l0) / 13
+    out["gray_sobel_pass_rgb_inplace_3840x2160x64"]["launches_per_pass"] = (pkg.launch_count() - l0) / (6 * npass)
+    out["gray_sobel_pass_rgb_inplace_3840x2160x64"]["passes_per_call"] = npass
+    sec1 = timeit(lambda: L.ompimg_gray_sobel_pass_dev(img.ptr, W * 3, 3, e.ptr, W, W, H, n5, PX * 3, PX, 0))
+    out["gray_sobel_pass_rgb_inplace_3840x2160x64"]["single_pass_call"] = entry(n5 * PX, 6, sec1)
     img.free(); e.free()
     # cfg4: 8192x8192 RGB box / binomial blur (uint8 out).  Device layout: rows 128-byte aligned like every device copy the host entry
     # points make (conv_tma.cuh: tensor-map copies); the reference's dense (cols+K-1)*3 pitch (conv_sep.cuh) is timed beside it.

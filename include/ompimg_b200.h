@@ -134,6 +134,11 @@ OMPIMG_API int ompimg_replicate_dev(const uint8_t *plane, size_t plane_pitch, ui
  * kernel (edge must then be given).  The host form always returns the edge plane in `edge` when it is not NULL. */
 OMPIMG_API int ompimg_gray_sobel_pass_dev(uint8_t *img, size_t img_pitch, int channels, uint8_t *edge, size_t edge_pitch,
                                int width, int height, int nframes, size_t img_stride, size_t edge_stride, int stream);
+/* the driver's whole loop, `for (p = 0; p < passes; p++)` around main_with_sobel.c:51-74, in place on img: on the fused path every
+ * pass but the last also writes what its successor needs (the rows and pixels either side of the kernel's band and strip seams), so
+ * only the first pass runs the preparation kernel: passes + 1 launches, 6 bytes/pixel each. */
+OMPIMG_API int ompimg_gray_sobel_passes_dev(uint8_t *img, size_t img_pitch, int channels, uint8_t *edge, size_t edge_pitch,
+                                 int width, int height, int nframes, size_t img_stride, size_t edge_stride, int passes, int stream);
 OMPIMG_API int ompimg_gray_sobel_pass_host(uint8_t *img, int width, int height, int channels, uint8_t *edge);
 
 /* batch of frames in host memory -> edge planes in host memory, H2D/kernel/D2H overlapped on

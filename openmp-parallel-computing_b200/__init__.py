@@ -92,6 +92,7 @@ _SIGS = {
     "ompimg_rgb_to_edge_band_dev": (C.c_int, [_vp, _sz, C.c_int, _vp, _sz, C.c_int, C.c_int, _vp, _vp, C.c_int]),
     "ompimg_replicate_dev": (C.c_int, [_vp, _sz, _vp, _sz, C.c_int, C.c_int, C.c_int, C.c_int, _sz, _sz, C.c_int]),
     "ompimg_gray_sobel_pass_dev": (C.c_int, [_vp, _sz, C.c_int, _vp, _sz, C.c_int, C.c_int, C.c_int, _sz, _sz, C.c_int]),
+    "ompimg_gray_sobel_passes_dev": (C.c_int, [_vp, _sz, C.c_int, _vp, _sz, C.c_int, C.c_int, C.c_int, _sz, _sz, C.c_int, C.c_int]),
     "ompimg_gray_sobel_pass_host": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp]),
     "ompimg_rgb_to_edge_batch_host": (C.c_int, [_vp, _sz, C.c_int, _vp, _sz, C.c_int, C.c_int, C.c_int]),
     "ompimg_conv_i32_dev": (C.c_int, [_vp, _sz, C.c_int, C.c_int, C.c_int, _vp, C.c_int32, _vp, _sz, C.c_int]),

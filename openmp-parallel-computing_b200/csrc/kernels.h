@@ -61,8 +61,9 @@ cudaError_t launch_sobel(const StencilArgs &a, int sm_count, cudaStream_t st);
 struct PassScratch { size_t row_pitch, rows_bytes, border_bytes, entry_pitch, entries_bytes; size_t total() const { return rows_bytes + border_bytes + entries_bytes; } };
 bool pass_inplace_supported(const uint8_t *img, size_t pitch, size_t stride, int w, int h, int ch, int nframes);
 PassScratch pass_inplace_scratch(int w, int h, int nframes, int sm_count);
+// `passes` iterations; scratch: sz.total() bytes for one pass, 2 * sz.total() for more
 cudaError_t launch_gray_sobel_pass_inplace(uint8_t *img, size_t pitch, size_t stride, int w, int h, int nframes, const uint8_t *edge, size_t epitch,
-                                           size_t estride, int fma_mode, int no_bias, uint8_t *scratch, int sm_count, cudaStream_t st);
+                                           size_t estride, int fma_mode, int no_bias, int passes, uint8_t *scratch, int sm_count, cudaStream_t st);
 int sqrt_exact_flag();          // runtime.cu: 1 when the bound device passed the exhaustive MUFU.SQRT check
 cudaError_t launch_isqrt_selftest(uint8_t *out_dev, unsigned int count, float bias, cudaStream_t st);
 

@@ -504,29 +504,37 @@ extern "C" int ompimg_replicate_dev(const uint8_t *plane, size_t pp, uint8_t *im
     CK(launch_replicate(plane, pp, img, ip, ch, w, h, nframes, ps, is, g.sm_count, st));
     return OMPIMG_OK;
 }
-extern "C" int ompimg_gray_sobel_pass_dev(uint8_t *img, size_t ip, int ch, uint8_t *edge, size_t ep, int w, int h, int nframes,
-                                          size_t is, size_t es, int stream) {
+extern "C" int ompimg_gray_sobel_passes_dev(uint8_t *img, size_t ip, int ch, uint8_t *edge, size_t ep, int w, int h, int nframes,
+                                            size_t is, size_t es, int passes, int stream) {
     INIT(); STREAM(stream, st);
-    NEED(img && w > 0 && h > 0 && nframes > 0, "image");
+    NEED(img && w > 0 && h > 0 && nframes > 0 && passes >= 0, "image");
     NEED(ch == 3 || ch == 4, "channels must be 3 or 4");
     NEED(ip >= (size_t)w * ch && (!edge || ep >= (size_t)w), "pitch");
+    if (passes == 0) return OMPIMG_OK;
     if (w >= 3 && h >= 3 && pass_inplace_supported(img, ip, is, w, h, ch, nframes)) {
         // 3 channels, 16-byte friendly layout: a preparation kernel saves what the in-place kernel could find overwritten,
-        // then ONE fused kernel reads RGB and writes the replicated edge value back over it (6 bytes/pixel moved).  The
-        // scratch plane's border bytes are read (they become the image border); its interior is not written -- no edge plane
-        // ever exists on this path.  The side buffers belong to the stream: passes on different streams do not share them.
+        // then ONE fused kernel per pass reads RGB and writes the replicated edge value back over it (6 bytes/pixel moved); every
+        // pass but the last also writes what its successor needs, so n passes are 1 + n launches.  The scratch plane's border
+        // bytes are read (they become the image border); its interior is not written -- no edge plane ever exists on this path.
+        // The side buffers belong to the stream: passes on different streams do not share them.
         std::lock_guard<std::recursive_mutex> lk(g.mu);
         const PassScratch sz = pass_inplace_scratch(w, h, nframes, g.sm_count);
-        RESERVE(g.pass_scratch[stream], sz.total() + 256);
-        CK(launch_gray_sobel_pass_inplace(img, ip, is, w, h, nframes, edge, ep, es, g.luma_mode, g.sqrt_exact, (uint8_t *)g.pass_scratch[stream].p,
+        RESERVE(g.pass_scratch[stream], (passes > 1 ? 2 : 1) * sz.total() + 256);
+        CK(launch_gray_sobel_pass_inplace(img, ip, is, w, h, nframes, edge, ep, es, g.luma_mode, g.sqrt_exact, passes, (uint8_t *)g.pass_scratch[stream].p,
                                           g.sm_count, st));
         return OMPIMG_OK;
     }
     NEED(edge, "this layout (4 channels, or rows that are not 16-byte friendly) needs the scratch plane");
-    int rc = sobel_common(img, ip, ch, edge, ep, w, h, nframes, is, es, nullptr, nullptr, st);
-    if (rc) return rc;
-    CK(launch_replicate(edge, ep, img, ip, ch, w, h, nframes, es, is, g.sm_count, st));
+    for (int ps = 0; ps < passes; ++ps) {
+        int rc = sobel_common(img, ip, ch, edge, ep, w, h, nframes, is, es, nullptr, nullptr, st);
+        if (rc) return rc;
+        CK(launch_replicate(edge, ep, img, ip, ch, w, h, nframes, es, is, g.sm_count, st));
+    }
     return OMPIMG_OK;
+}
+extern "C" int ompimg_gray_sobel_pass_dev(uint8_t *img, size_t ip, int ch, uint8_t *edge, size_t ep, int w, int h, int nframes,
+                                          size_t is, size_t es, int stream) {
+    return ompimg_gray_sobel_passes_dev(img, ip, ch, edge, ep, w, h, nframes, is, es, 1, stream);
 }
 extern "C" int ompimg_conv_i32_dev(const uint8_t *in, size_t in_pitch, int rows, int cols, int K, const int32_t *taps, int32_t norm,
                                    int32_t *out, size_t out_pitch, int stream) {

@@ -73,6 +73,7 @@ struct PassSide {
     const uint8_t *entries_base;    // [frame][row][entries] x 16 bytes: (pixel left of strip boundary k, pixel right of it, 8 unused), RGB in bytes 0..2 / 4..6
     size_t entry_pitch;             // bytes per row of entries (multiple of 16)
     int entries;                    // nstrips + 1
+    uint8_t *next_rows, *next_entries;      // the other set (written by this pass for the next one) or nullptr
 };
 
 struct TmaStencilParams {
@@ -86,6 +87,11 @@ struct TmaStencilParams {
     const uint8_t *side_rows; // [frame][band][first, last source row][side_row_pitch]
     size_t side_row_pitch;
     const uint8_t *border_rows;   // [frame][top, bottom][side_row_pitch]: what image rows 0 and height-1 become (scratch plane's border rows, replicated)
+    // MODE 2 with more passes to come (ompimg_gray_sobel_passes_dev): this pass writes, next to its output, what the NEXT pass needs at the
+    // places pass_prepare_kernel saved for this one (a second set of side buffers, same layout), so only the first pass needs a preparation
+    uint8_t *next_rows;       // [frame][band][first, last source row][side_row_pitch], or nullptr
+    uint8_t *next_entries;    // [frame][row][nstrips+1] x 16 bytes, or nullptr
+    size_t entry_pitch;
     int width, height;
     int nbands, rows_per_band, nstrips;
     int fold;                 // the last strip is at most 256 pixels wide: one warp takes it for two bands
@@ -360,6 +366,13 @@ __global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? 3 : 2) sobel_tma_kern
     uint8_t *out = p.dst + (size_t)frame * p.dst_stride + ((ptrdiff_t)rin0 - 1) * (ptrdiff_t)p.dst_pitch + (size_t)x0 * (RGBOUT ? 3 : 1);   // stores go one row above the source row being consumed
     const uint32_t side_off = ec.mL ? 0u : 20u;         // RGBOUT: the strip-edge pixel of this lane in a side-box row (first lane: left one, last lane: right one)
     uint32_t side_prev = 0;                             // ... and the previous row's, whose low byte is that row's border value in the outermost lanes
+    // next pass's side data: lane 0 writes the pixel right of strip boundary `strip` (its first pixel), lane 31 the pixel left of boundary
+    // `strip + 1` (its last pixel, when the image reaches that far), of every row this warp writes
+    const bool ent_lane = RGBOUT && p.next_entries != nullptr && (lane == 0 || (lane == 31 && xs + 511 < p.width));
+    uint8_t *ent = nullptr;
+    if (RGBOUT && ent_lane)
+        ent = p.next_entries + ((ptrdiff_t)frame * p.height + rin0 - 1) * (ptrdiff_t)p.entry_pitch + (lane == 0 ? strip * 16 + 4 : (strip + 1) * 16);      // like `out`: one row above the source row being consumed
+    const size_t ent_pitch = RGBOUT ? p.entry_pitch : 0;
     float half = BIAS ? 0.5f : 0.0f;
     if (BIAS) asm volatile("" : "+f"(half));
 
@@ -410,9 +423,22 @@ __global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? 3 : 2) sobel_tma_kern
                     if (npx == 16) store_rgb48(out, o);
                     else store_rgb_partial(out, o, npx);
                 }
+                if (ent_lane) *reinterpret_cast<uint32_t *>(ent) = (lane == 0 ? (o.x & 255u) : (o.w >> 24)) * 0x010101u;
+                if (CHECKED && p.next_rows != nullptr && mode) {
+                    // this band's first output row is the previous band's last source row, its last output row the next band's first one
+                    const int i = 3 * t + RHO;
+                    if (i == 2 && band_a >= 1) {
+                        uint8_t *q = p.next_rows + (((size_t)frame * p.nbands + (band_a - 1)) * 2 + 1) * p.side_row_pitch + (size_t)x0 * 3;
+                        if (npx == 16) store_rgb48(q, o); else store_rgb_partial(q, o, npx);
+                    }
+                    if (i == nin - 1 && band_a + 1 < p.nbands) {
+                        uint8_t *q = p.next_rows + (((size_t)frame * p.nbands + (band_a + 1)) * 2 + 0) * p.side_row_pitch + (size_t)x0 * 3;
+                        if (npx == 16) store_rgb48(q, o); else store_rgb_partial(q, o, npx);
+                    }
+                }
             }
         }
-        if (RGBOUT) side_prev = raw.e0;
+        if (RGBOUT) { side_prev = raw.e0; ent += ent_pitch; }
         out += dpitch;
     };
     auto trip = [&](auto checked_c, int t) {
@@ -433,11 +459,23 @@ __global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? 3 : 2) sobel_tma_kern
             if (which == 0 ? a0 != 0 : a1 != p.height - 1) continue;
             const uint8_t *sr = brow + (size_t)which * p.side_row_pitch;
             uint8_t *dr = irow + (size_t)(which ? p.height - 1 : 0) * p.dst_pitch;
+            // ... and, for the next pass, the same row as band 0's first / the last band's last source row, and its strip-boundary entries
+            uint8_t *nr = p.next_rows ? p.next_rows + (((size_t)frame * p.nbands + band_a) * 2 + which) * p.side_row_pitch + (size_t)x0 * 3 : nullptr;
             if (npx == 16) {
 #pragma unroll
-                for (int q = 0; q < 3; ++q) reinterpret_cast<uint4 *>(dr)[q] = reinterpret_cast<const uint4 *>(sr)[q];
+                for (int q = 0; q < 3; ++q) {
+                    const uint4 v = reinterpret_cast<const uint4 *>(sr)[q];
+                    reinterpret_cast<uint4 *>(dr)[q] = v;
+                    if (nr) reinterpret_cast<uint4 *>(nr)[q] = v;
+                }
             } else {
-                for (int j = 0; j < 3 * npx; ++j) dr[j] = sr[j];
+                for (int j = 0; j < 3 * npx; ++j) { dr[j] = sr[j]; if (nr) nr[j] = sr[j]; }
+            }
+            if (ent_lane) {
+                const uint8_t *px = lane == 0 ? sr : sr + 45;
+                uint8_t *e = p.next_entries + ((size_t)frame * p.height + (size_t)(which ? p.height - 1 : 0)) * p.entry_pitch +
+                             (lane == 0 ? (size_t)strip * 16 + 4 : (size_t)(strip + 1) * 16);
+                *reinterpret_cast<uint32_t *>(e) = (uint32_t)px[0] | ((uint32_t)px[1] << 8) | ((uint32_t)px[2] << 16);
             }
         }
     }
@@ -532,6 +570,7 @@ static cudaError_t launch_sobel_tma_h(const StencilArgs &a, int sm_count, cudaSt
     if (MODE == 2) {
         if (!side) return cudaErrorInvalidValue;
         p.side_rows = side->rows; p.side_row_pitch = side->row_pitch; p.border_rows = side->border;
+        p.next_rows = side->next_rows; p.next_entries = side->next_entries; p.entry_pitch = side->entry_pitch;
         EncodeTiledFn enc = encode_tiled_fn();
         if (!enc) return cudaErrorNotSupported;
         const cuuint64_t dims[3] = {(cuuint64_t)side->entries * 2, (cuuint64_t)a.height, (cuuint64_t)a.nframes};      // uint64 elements
@@ -572,6 +611,7 @@ struct PrepParams {
     uint8_t *rows; size_t row_pitch;                     // out: [frame][band][2][row_pitch]
     uint8_t *border; /* out: [frame][2][row_pitch] */
     uint8_t *entries; size_t entry_pitch;                // out: [frame][row][nstrips+1] x 16 bytes
+    uint8_t *entries2;                                   // out (multi-pass runs): the other set's constant halves -- the row's border values in entry 0's left and the last entry's right pixel -- or nullptr
 };
 // Reads the image only; everything the in-place kernel could find overwritten is copied out first (see sobel_tma_kernel).
 // Three ranges of CTAs, no 64-bit divisions: [0, nA) copy every band's first and last source row (one thread per 16-byte chunk),
@@ -623,6 +663,11 @@ __global__ void __launch_bounds__(256) pass_prepare_kernel(const PrepParams p) {
         if (xb < (uint32_t)p.w) R = *reinterpret_cast<const uint32_t *>(row + (size_t)xb * 3) & 0xffffffu;
         else R = (er ? (uint32_t)er[p.w - 1] : 0u) * 0x010101u;
         *reinterpret_cast<uint4 *>(p.entries + (size_t)fy * p.entry_pitch + (size_t)k * 16) = make_uint4(L, R, 0u, 0u);
+        if (p.entries2) {
+            uint32_t *e2 = reinterpret_cast<uint32_t *>(p.entries2 + (size_t)fy * p.entry_pitch + (size_t)k * 16);
+            if (k == 0) e2[0] = L;
+            if (k == (uint32_t)p.nstrips) e2[1] = R;
+        }
     }
 }
 
@@ -644,35 +689,47 @@ template <int FMA_MODE, bool BIAS>
 static cudaError_t launch_pass_inplace_t(const StencilArgs &a, const PassSide &side, int sm_count, cudaStream_t st) {
     return launch_sobel_tma_h<3, FMA_MODE, BIAS, 2>(a, sm_count, st, &side);
 }
-// one iteration of main_with_sobel.c:51-74 in place on `img` (3 channels): scratch = rows | border | entries as sized by pass_inplace_scratch
+// `passes` iterations of main_with_sobel.c:51-74 in place on `img` (3 channels).  scratch = rows | border | entries [| rows | entries for
+// passes > 1] as sized by pass_inplace_scratch: the preparation kernel fills the first set from the image; every pass but the last
+// writes the other set for its successor, so a run of n passes is 1 + n launches.
 cudaError_t launch_gray_sobel_pass_inplace(uint8_t *img, size_t pitch, size_t stride, int w, int h, int nframes, const uint8_t *edge, size_t epitch,
-                                           size_t estride, int fma_mode, int no_bias, uint8_t *scratch, int sm_count, cudaStream_t st) {
+                                           size_t estride, int fma_mode, int no_bias, int passes, uint8_t *scratch, int sm_count, cudaStream_t st) {
+    if (passes < 1) return cudaSuccess;
     const TmaDecomp d = tma_decomp(w, h, nframes, 3, sm_count);
     const PassScratch sz = pass_inplace_scratch(w, h, nframes, sm_count);
+    uint8_t *rows[2] = {scratch, scratch + sz.total()};
+    uint8_t *border = scratch + sz.rows_bytes;
+    uint8_t *entries[2] = {scratch + sz.rows_bytes + sz.border_bytes, scratch + sz.total() + sz.rows_bytes};
     PrepParams pp{};
     pp.img = img; pp.pitch = pitch; pp.stride = stride; pp.w = w; pp.h = h; pp.nframes = nframes;
     pp.nbands = d.nbands; pp.rpb = d.rows_per_band; pp.nstrips = d.nstrips;
     pp.row_bytes16 = (uint32_t)sz.row_pitch;
     pp.edge = edge; pp.epitch = epitch; pp.estride = estride;
-    pp.rows = scratch; pp.row_pitch = sz.row_pitch;
-    pp.border = scratch + sz.rows_bytes;
-    pp.entries = scratch + sz.rows_bytes + sz.border_bytes; pp.entry_pitch = sz.entry_pitch;
+    pp.rows = rows[0]; pp.row_pitch = sz.row_pitch;
+    pp.border = border;
+    pp.entries = entries[0]; pp.entry_pitch = sz.entry_pitch;
+    pp.entries2 = passes > 1 ? entries[1] : nullptr;
     const long long cpr = ((long long)(sz.row_pitch / 16) + 255) / 256;
     const long long ctas = (long long)nframes * (d.nbands + 1) * 2 * cpr + ((long long)nframes * h * (d.nstrips + 1) + 255) / 256;
     if (ctas > 0x7fffffffLL || (long long)nframes * h > 0xffffffffLL) return cudaErrorInvalidValue;
-    const int grid = (int)ctas;
     count_launch();
-    pass_prepare_kernel<<<grid, 256, 0, st>>>(pp);
+    pass_prepare_kernel<<<(int)ctas, 256, 0, st>>>(pp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     StencilArgs a{};
     a.src = img; a.dst = img; a.src_pitch = pitch; a.dst_pitch = pitch; a.src_stride = stride; a.dst_stride = stride;
     a.width = w; a.height = h; a.channels = 3; a.nframes = nframes; a.fma_mode = fma_mode; a.no_bias = no_bias;
-    PassSide side{};
-    side.rows = pp.rows; side.row_pitch = sz.row_pitch; side.border = pp.border;
-    side.entries_base = pp.entries; side.entry_pitch = sz.entry_pitch; side.entries = d.nstrips + 1;
-    if (no_bias) return fma_mode ? launch_pass_inplace_t<1, false>(a, side, sm_count, st) : launch_pass_inplace_t<0, false>(a, side, sm_count, st);
-    return fma_mode ? launch_pass_inplace_t<1, true>(a, side, sm_count, st) : launch_pass_inplace_t<0, true>(a, side, sm_count, st);
+    for (int ps = 0; ps < passes; ++ps) {
+        const int cur = ps & 1, more = ps + 1 < passes;
+        PassSide side{};
+        side.rows = rows[cur]; side.row_pitch = sz.row_pitch; side.border = border;
+        side.entries_base = entries[cur]; side.entry_pitch = sz.entry_pitch; side.entries = d.nstrips + 1;
+        side.next_rows = more ? rows[cur ^ 1] : nullptr; side.next_entries = more ? entries[cur ^ 1] : nullptr;
+        if (no_bias) e = fma_mode ? launch_pass_inplace_t<1, false>(a, side, sm_count, st) : launch_pass_inplace_t<0, false>(a, side, sm_count, st);
+        else e = fma_mode ? launch_pass_inplace_t<1, true>(a, side, sm_count, st) : launch_pass_inplace_t<0, true>(a, side, sm_count, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 // ---------------------------------------------------------------------------------------------

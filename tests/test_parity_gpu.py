@@ -393,6 +393,45 @@ def test_gray_sobel_pass_dev_other_layouts_take_two_kernels(gpu, O):
         img.free(); ebuf.free()
 
 
+@pytest.mark.parametrize("h,w,nframes", [(1080, 1920, 2), (257, 1500, 1), (64, 2037, 2), (131, 512, 1), (40, 1024, 1), (3, 3, 1), (5, 17, 2), (4, 16, 1),
+                                         (262, 4112, 1), (133, 513, 1), (700, 3840, 1), (19, 8191, 1)])
+def test_gray_sobel_passes_dev_multi_pass(gpu, O, h, w, nframes):
+    """the driver's loop on the device (main_with_sobel.c:51-74 x passes) through ompimg_gray_sobel_passes_dev: every pass but the last
+    writes the next pass's seam data itself (one preparation kernel for the whole run).  1, 2, 3 and 6 passes against the oracle's
+    repeated pass, absent / zero / non-zero scratch border, both luma modes, widths on and off the 512-pixel strip grid."""
+    L = gpu.lib()
+    pitch, epitch = (w * 3 + 127) // 128 * 128, (w + 127) // 128 * 128
+    rng = np.random.default_rng(h * 7919 + w)
+    for mode, border in (("strict", 0xAB), ("fma", None), ("strict", 0)):
+        gpu.set_luma_mode(mode)
+        try:
+            frames = rng.integers(0, 256, (nframes, h, w, 3), dtype=np.uint8)
+            edge_host = None
+            if border is not None:
+                edge_host = np.zeros((nframes, h, w), np.uint8)
+                if border:
+                    edge_host[:, 0, :] = rng.integers(0, 256, (nframes, w)); edge_host[:, -1, :] = rng.integers(0, 256, (nframes, w))
+                    edge_host[:, :, 0] = rng.integers(0, 256, (nframes, h)); edge_host[:, :, -1] = rng.integers(0, 256, (nframes, h))
+            for passes in (1, 2, 3, 6):
+                want = frames.copy()
+                for f in range(nframes):
+                    e = edge_host[f].copy() if edge_host is not None else np.zeros((h, w), np.uint8)
+                    for _ in range(passes):
+                        want[f], e = O.gray_sobel_pass(want[f].copy(), e, fma=(mode == "fma"))
+                img = to_dev_pitched(gpu, frames.reshape(nframes * h, w * 3), pitch)
+                ebuf = to_dev_pitched(gpu, edge_host.reshape(nframes * h, w), epitch) if edge_host is not None else None
+                ck(gpu, L.ompimg_gray_sobel_passes_dev(img.ptr, pitch, 3, ebuf.ptr if ebuf else None, epitch, w, h, nframes, pitch * h, epitch * h, passes, 0))
+                gpu.sync(0)
+                raw = from_dev_pitched(gpu, img, nframes * h, pitch, pitch)
+                assert np.array_equal(raw[:, :w * 3].reshape(nframes, h, w, 3), want), (mode, border, passes)
+                assert (raw[:, w * 3:] == 0xCD).all(), "row padding was written"
+                img.free()
+                if ebuf:
+                    ebuf.free()
+        finally:
+            gpu.set_luma_mode("strict")
+
+
 def test_row_bands_on_distinct_devices_equal_oracle(gpu, O):
     """the real peer path: every band on its own GPU, halo rows fetched by the kernel's bulk copies over NVLink
     (skips on a one-GPU box; `gpurun --gpus 2` and the 8-GPU scaling run exercise it)"""

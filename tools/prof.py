@@ -70,6 +70,11 @@ def main():
         pkg.synth_dev(src, src.nbytes, 3); dst.fill(0)
         fn = lambda: L.ompimg_gray_sobel_pass_dev(src.ptr, W * 3, 3, dst.ptr, W, W, H, n, px * 3, px, 0)
         bpp = 6
+    elif a.kernel == "passes":                           # the driver's loop: 8 passes per call, one preparation kernel
+        src, dst = pkg.DeviceBuffer(n * px * 3), pkg.DeviceBuffer(n * px)
+        pkg.synth_dev(src, src.nbytes, 3); dst.fill(0)
+        fn = lambda: L.ompimg_gray_sobel_passes_dev(src.ptr, W * 3, 3, dst.ptr, W, W, H, n, px * 3, px, 8, 0)
+        bpp = 6 * 8
     elif a.kernel in ("conv5", "conv9", "conv5g", "conv9g"):
         K = int(a.kernel[4])
         rows = cols = 8192
