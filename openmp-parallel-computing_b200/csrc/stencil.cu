@@ -521,20 +521,22 @@ struct TmaDecomp { int nstrips, rows_per_band, nbands; };
 static TmaDecomp tma_decomp(int width, int height, int nframes, int ch, int sm_count) {
     TmaDecomp d;
     d.nstrips = (width + 511) / 512;
-    // Band height (1 mod 3: each band then consumes a multiple of three source rows).  A launch of T tasks runs in F = ceil(T / slots)
-    // waves on the resident warp slots (24 per SM for planes, 16 for RGB(A)).  With one wave the launch lasts as long as its tallest
-    // band plus the two priming rows every band re-reads; with many waves early finishers pick up new tasks and only the total work
-    // W (rows + 2 summed over the tasks) counts.  Estimate W/slots + (F*(c+2) - W/slots)/F, exact at F = 1 and -> W/slots for large F,
-    // and take the height that minimises it (ties: the taller band).
-    int rpb = 130;
+    // Band height (1 mod 3: each band then consumes a multiple of three source rows), chosen to waste least: every band
+    // re-reads two rows and primes on two rows (2/rows extra), and a launch of T tasks on the resident warp slots
+    // (24 per SM for planes, 16 for RGB(A)) runs in ceil(T/slots) waves of which the last is only partly full.
+    // Launches of fewer than ~5 waves do not consider bands taller than 64 rows: in more, shorter waves the warps of an SM drift
+    // apart and keep the memory system evenly loaded, which is worth more than the 2/rows saved -- 64 4K frames: fused 1381 Gpx/s
+    // with the 112-row bands the estimate alone picks, 1431-1460 with 40-64 rows; planes 2479 -> 2523, 2000x3000 planes 2376 -> 2478.
+    // Long launches keep the tall bands (256 frames, 32768^2: 2 % better with 94-130 rows; tools/prof.py, OMPIMG_SOBEL_BAND).
     const double slots = (double)sm_count * (ch == 1 ? 24 : 16);
+    const int cmax = (double)nframes * d.nstrips * ((height - 1 + 129) / 130) < 5.0 * slots ? 64 : 130;
+    int rpb = cmax;
     double best = -1.0;
-    for (int c = 130; c >= 16; c -= 3) {
-        const long long nb = (height - 1 + c - 1) / c;
-        const double tasks = (double)nframes * d.nstrips * nb, full = (double)(long long)((tasks + slots - 1) / slots);
-        const double work = (double)nframes * d.nstrips * ((double)(height - 1) + 2.0 * nb) / slots;
-        const double span = work + (full * (c + 2) - work) / full;
-        if (best < 0 || span < best * 0.999) { best = span; rpb = c; }
+    for (int c = cmax; c >= 16; c -= 3) {
+        const double tasks = (double)nframes * d.nstrips * ((height - 1 + c - 1) / c);
+        const double waves = tasks / slots, full = waves <= 1.0 ? 1.0 : (double)(long long)(waves + 0.999999);
+        const double eff = waves / full * (double)c / (double)(c + 2);
+        if (eff > best * 1.005) { best = eff; rpb = c; }        // ties go to the taller band
     }
     { static int env = -1; if (env < 0) { const char *e = getenv("OMPIMG_SOBEL_BAND"); env = e ? atoi(e) : 0; } if (env > 0) rpb = env; }
     d.rows_per_band = rpb;
