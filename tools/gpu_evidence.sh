@@ -29,5 +29,6 @@ cap conv9g conv_tma "conv9g"
 cap sobel2000 sobel_tma "sobel --width 2000 --height 3000 --frames 128"
 cap sobel4k sobel_tma "sobel --width 3840 --height 2160 --frames 64"
 cap pass sobel_tma "pass"
+cap passes sobel_tma "passes"
 cap gray stream_kernel "gray"
 tail -3 $o/${tag}_gputest.log
