@@ -59,7 +59,7 @@ struct ConvTmaParams {
     int32_t norm;                // unused here (signed taps take conv_sep.cuh); read by the shared lane code's DIV 2 branch only
 };
 
-// band geometry is chosen by the launcher from the kernel's occupancy (conv_tma.cu passes everything else)
+// band geometry and ring depth are chosen by the launcher from the kernel's occupancy (conv_sep.cu passes everything else)
 template <int K>
 cudaError_t launch_conv_tma_k(ConvTmaParams &p, int out_u8, int div, int vbox, int sm_count, cudaStream_t st);
 
