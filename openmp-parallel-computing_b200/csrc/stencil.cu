@@ -384,9 +384,10 @@ __global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? 3 : 2) sobel_tma_kern
     uint32_t ph = 0;
 
     // one source row: load, (after the stage's last row: release the stage by requesting its refill,) arithmetic, store
-    auto row = [&](auto rho_c, auto checked_c, uint32_t addr, int t) {
+    auto row = [&](auto rho_c, auto checked_c, auto edge_c, uint32_t addr, int t) {
         constexpr int RHO = decltype(rho_c)::value;
         constexpr bool CHECKED = decltype(checked_c)::value;
+        constexpr bool EDGE = decltype(edge_c)::value;           // this warp holds a group on the image border (warp-uniform, fixed for the task)
         if (SUBST && CHECKED) {
             if (use_above && t == 0 && RHO == 0) addr = my_halo;
             if (use_below && t == below_t && RHO == below_rho) addr = my_halo + G::HALO_SLOT;
@@ -409,11 +410,11 @@ __global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? 3 : 2) sobel_tma_kern
             uint4 o = sobel_mag16(gx, gy, half);                    // once per row, whatever the lanes' store modes
             if (!RGBOUT) {
                 if (mode == 1) *reinterpret_cast<uint4 *>(out) = o;
-                if (edge_warp) {
+                if (EDGE) {
                     if (mode >= 2) store_edge16(out, o, mode, plast);
                 }
             } else {
-                if (edge_warp) {
+                if (EDGE) {
                     // the image border takes the scratch plane's border values of the OUTPUT row (the previous source row's side entries)
                     const uint32_t br = __shfl_sync(0xffffffffu, side_prev, 31) & 255u;
                     if (mode == 2 || mode == 4) o.x = (o.x & 0xffffff00u) | (side_prev & 255u);
@@ -441,12 +442,12 @@ __global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? 3 : 2) sobel_tma_kern
         if (RGBOUT) { side_prev = raw.e0; ent += ent_pitch; }
         out += dpitch;
     };
-    auto trip = [&](auto checked_c, int t) {
+    auto trip = [&](auto checked_c, auto edge_c, int t) {
         mbar_wait(bar0 + 8 * s, ph);
         const uint32_t a = my + (uint32_t)s * STAGE;
-        row(IntC<0>{}, checked_c, a, t);
-        row(IntC<1>{}, checked_c, a + rs, t);
-        row(IntC<2>{}, checked_c, a + 2 * rs, t);
+        row(IntC<0>{}, checked_c, edge_c, a, t);
+        row(IntC<1>{}, checked_c, edge_c, a + rs, t);
+        row(IntC<2>{}, checked_c, edge_c, a + 2 * rs, t);
         if (++s == S) { s = 0; ph ^= 1; }
     };
 
@@ -483,10 +484,13 @@ __global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? 3 : 2) sobel_tma_kern
     // trips [1, tsteady) lie entirely inside every storing lane's band and hold no substituted row
     int tsteady = (has_b ? min(nin_a, nin_b) : nin_a) / 3;
     if (SUBST && use_below) tsteady = min(tsteady, below_t);
-    trip(BoolC<true>{}, 0);
+    // warps without a border group (six of a 4K row's eight strips) run a steady body with no border-store code at all
+    // (not the in-place RGB mode: a third copy of its larger body costs more in instruction fetch than it saves -- 119 -> 98 Gpx/s)
+    trip(BoolC<true>{}, BoolC<true>{}, 0);
     int t = 1;
-    for (; t < tsteady; ++t) trip(BoolC<false>{}, t);
-    for (; t < ntrips; ++t) trip(BoolC<true>{}, t);
+    if (RGBOUT || edge_warp) for (; t < tsteady; ++t) trip(BoolC<false>{}, BoolC<true>{}, t);
+    else for (; t < tsteady; ++t) trip(BoolC<false>{}, BoolC<RGBOUT>{}, t);
+    for (; t < ntrips; ++t) trip(BoolC<true>{}, BoolC<true>{}, t);
 }
 
 // cuTensorMapEncodeTiled comes from the driver through the runtime (the library links the static runtime only)
