@@ -76,9 +76,12 @@ struct ConvLane {
     // Two consecutive input rows (w[0], w[1]) at ring slot S.  p: the kernel's parameter block (th, ut, magic, shift, norm).
     // emit: the rows complete output rows (orow, orow + opitch); two: the second of them exists.  stg / stg_rd: this lane's
     // write / read address in the warp's staging buffer.  The caller advances orow by two rows when emit.
-    template <int S, typename P>
-    __device__ __forceinline__ void rows2(const uint32_t (&w)[2][NWRD], const P &p, bool emit, bool two, bool wide, int lval, int lane,
+    // WIDE_ONLY: the caller guarantees `wide` (its steady loop): the per-lane store code is not generated at all, which keeps the
+    // unrolled hot block small (instruction fetch is a limit for the K = 9 bodies).
+    template <int S, bool WIDE_ONLY = false, typename P>
+    __device__ __forceinline__ void rows2(const uint32_t (&w)[2][NWRD], const P &p, bool emit, bool two, bool wide_in, int lval, int lane,
                                           uint32_t stg, uint32_t stg_rd, uint8_t *orow, size_t opitch) {
+        const bool wide = WIDE_ONLY ? true : wide_in;
         uint32_t h[2][12];
 #pragma unroll
         for (int rho = 0; rho < 2; ++rho) {

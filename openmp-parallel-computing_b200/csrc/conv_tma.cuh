@@ -16,7 +16,8 @@
 // Loop structure.  A band's trips (two input rows each) run in blocks of NP = (K+1)/2 trips, so that the
 // ring slot of the vertical window is a compile-time register.  The first block (K-1 priming rows, first
 // outputs) and the last trips of the band run a "checked" body; every block in between runs a body with
-// no per-trip tests (emit, second-row-valid, trip-exists).
+// no per-trip tests (emit, second-row-valid, trip-exists) and, being entered only by warps whose output leaves as whole
+// 16-byte pieces, no per-lane store code.
 //
 // Arithmetic per lane (4 pixels = 12 output bytes) and input row: conv_lane.cuh (shared with conv_sep.cuh).
 // Instruction budget and the pipe that bounds each K: DESIGN.md 4.3.
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(CT_WARPS * 32, K <= 5 ? CT_MINB_LO : (VBOX ? C
 
         const bool emit = !CHECKED || t >= NP - 1;
         const bool two = !CHECKED || ro + 1 < yb;
-        L.template rows2<s>(w, p, emit, two, wide, lval, lane, stg, stg_rd, orow, opitch);
+        L.template rows2<s, !CHECKED>(w, p, emit, two, wide, lval, lane, stg, stg_rd, orow, opitch);      // unchecked blocks run for `wide` warps only
         if (emit) {
             orow += 2 * opitch;
             ro += 2;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(CT_WARPS * 32, K <= 5 ? CT_MINB_LO : (VBOX ? C
     // block 0 primes the window; blocks whose trips all exist and all emit two rows run unchecked; the rest checked
     const int tfull = (nout >> 1) + NP - 1;        // trips [NP-1, tfull) emit two rows each
     block(CtBool<true>{});
-    while (t0 + NP <= tfull) block(CtBool<false>{});
+    while (wide && t0 + NP <= tfull) block(CtBool<false>{});      // ragged strips / unaligned output rows stay on the checked body
     while (t0 < ntrips) block(CtBool<true>{});
 }
 
