@@ -30,11 +30,20 @@
 
 namespace ompimg {
 
-#ifndef CT_MINB_LO
-#define CT_MINB_LO 5                     // resident CTAs per SM the K <= 5 kernels are compiled for
+// resident CTAs per SM the kernels are compiled for (launch bounds -> register budget).  Measured (tools/conv_ab.sh): the 9x9 kernels
+// want registers rather than warps -- box 676 Gpx/s at 4 CTAs, 722 at 3; binomial 502 at 5 (tiny spills), 553 at 4, 591 at 3 --
+// the 5x5 box 811 at 5, 831 at 4, the 5x5 binomial 824 at 5, 817 at 4.
+#ifndef CT_MINB_5BOX
+#define CT_MINB_5BOX 4
 #endif
-#ifndef CT_MINB_HI
-#define CT_MINB_HI 4                     // ... and the K >= 7 kernels
+#ifndef CT_MINB_5GEN
+#define CT_MINB_5GEN 5
+#endif
+#ifndef CT_MINB_9BOX
+#define CT_MINB_9BOX 3
+#endif
+#ifndef CT_MINB_9GEN
+#define CT_MINB_9GEN 3
 #endif
 constexpr int CT_WARPS = 4;              // warps (tasks) per CTA
 constexpr int CT_LPX = CL_LPX;           // output pixels per lane
@@ -80,7 +89,7 @@ template <bool B> struct CtBool { static constexpr bool value = B; };
 // DIV: 0 acc >> shift | 1 umulhi(acc, magic) | 3 byte 1 (norm 256, u8 out) | 4 byte 2 (norm 65536, u8 out); taps >= 0.
 // VBOX (DIV 0 or 1 only): constant vertical taps, running window sums.
 template <int K, bool OUT_U8, int DIV, bool VBOX>
-__global__ void __launch_bounds__(CT_WARPS * 32, K <= 5 ? CT_MINB_LO : (VBOX ? CT_MINB_HI : CT_MINB_HI + 1)) conv_tma_kernel(const __grid_constant__ ConvTmaParams p) {
+__global__ void __launch_bounds__(CT_WARPS * 32, K <= 5 ? (VBOX ? CT_MINB_5BOX : CT_MINB_5GEN) : (VBOX ? CT_MINB_9BOX : CT_MINB_9GEN)) conv_tma_kernel(const __grid_constant__ ConvTmaParams p) {
     using Lane = ConvLane<K, OUT_U8, DIV, VBOX>;
     constexpr int NP = Lane::NP;                    // trips per block; pair-rows in the vertical window
     constexpr int NWRD = Lane::NWRD;                // 32-bit words that hold a lane's 4+K-1 input pixels
@@ -209,9 +218,7 @@ cudaError_t launch_conv_tma_k(ConvTmaParams &p, int out_u8, int div, int vbox, i
         // many waves early finishers pick up new tasks and only the total work W (rows + K-1 summed over the tasks) counts.  Estimate
         // W/slots + (F*(c+K-1) - W/slots)/F, exact at F = 1 and -> W/slots for large F, and take the height that minimises it (ties:
         // the taller band).
-        // K >= 7: tasks for four CTAs per SM measured best even where five fit (the IDP pipe is saturated by 16 warps; a fifth CTA
-        // splits the same throughput and adds a band's worth of re-filtered rows): 9x9 binomial 474 Gpx/s with 5, 503-537 with 4
-        const double slots = (double)sm_count * (K >= 7 ? min(occ, 4) : occ) * CT_WARPS;
+        const double slots = (double)sm_count * occ * CT_WARPS;
         int rpb = 2;
         double best = -1.0;
         for (int c = 512; c >= 2 * K; c -= 2) {
