@@ -29,10 +29,10 @@ def main():
         name = names.get(mangled, mangled)
         if not any(p.search(name) for p in pats):
             continue
-        lines = [l for l in blk.splitlines() if re.search(r"/\*[0-9a-f]{4}\*/", l)]
+        lines = [l for l in blk.splitlines() if re.search(r"/\*[0-9a-f]{4,6}\*/", l)]
         ops = collections.Counter()
         for l in lines:
-            m = re.search(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", l)
+            m = re.search(r"/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", l)
             if m:
                 ops[m.group(1).split(".")[0]] += 1
         print(f"\n== {name}\n   {len(lines)} instructions; static opcode counts: " + ", ".join(f"{k} {v}" for k, v in ops.most_common(14)))
