@@ -49,6 +49,12 @@ namespace ompimg {
 // the image-border values of the row in the outermost entries).  The kernel takes (a) into the spare row slots like
 // row-band mode does and (b) with one more 96-byte tensor box per stage, and never looks at the halo blocks of its stages.
 // ---------------------------------------------------------------------------------------------
+#ifndef SOBEL_MINB_PLANE
+#define SOBEL_MINB_PLANE 3                  // resident CTAs per SM the plane kernel is compiled for (80 registers): 2547 Gpx/s on 4K planes; 2 (96 registers) 2352, 4 (64, spills) 2058
+#endif
+#ifndef SOBEL_MINB_RGB
+#define SOBEL_MINB_RGB 2                    // ... and the RGB(A) kernels (128 registers; shared memory allows no more): fused 1432 Gpx/s, 1 CTA 1378
+#endif
 constexpr int TW_WARPS = 8;
 constexpr uint32_t round128(uint32_t v) { return (v + 127u) & ~127u; }
 template <int CH>
@@ -229,7 +235,7 @@ template <int N> struct IntC { static constexpr int value = N; };
 template <bool B> struct BoolC { static constexpr bool value = B; };
 
 template <int CH, int FMA_MODE, bool BIAS, int MODE>
-__global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? 3 : 2) sobel_tma_kernel(const __grid_constant__ TmaStencilParams p) {
+__global__ void __launch_bounds__(TW_WARPS * 32, CH == 1 ? SOBEL_MINB_PLANE : SOBEL_MINB_RGB) sobel_tma_kernel(const __grid_constant__ TmaStencilParams p) {
     using G = TmaGeom<CH>;
     constexpr bool HALO = MODE == 1, RGBOUT = MODE == 2, SUBST = MODE != 0;
     static_assert(!RGBOUT || CH == 3, "in-place RGB output is built for 3 channels");
@@ -532,7 +538,7 @@ static TmaDecomp tma_decomp(int width, int height, int nframes, int ch, int sm_c
     // apart and keep the memory system evenly loaded, which is worth more than the 2/rows saved -- 64 4K frames: fused 1381 Gpx/s
     // with the 112-row bands the estimate alone picks, 1431-1460 with 40-64 rows; planes 2479 -> 2523, 2000x3000 planes 2376 -> 2478.
     // Long launches keep the tall bands (256 frames, 32768^2: 2 % better with 94-130 rows; tools/prof.py, OMPIMG_SOBEL_BAND).
-    const double slots = (double)sm_count * (ch == 1 ? 24 : 16);
+    const double slots = (double)sm_count * TW_WARPS * (ch == 1 ? SOBEL_MINB_PLANE : SOBEL_MINB_RGB);
     const int cmax = (double)nframes * d.nstrips * ((height - 1 + 129) / 130) < 5.0 * slots ? 64 : 130;
     int rpb = cmax;
     double best = -1.0;
