@@ -27,6 +27,7 @@ namespace ompimg {
 constexpr int CL_LPX = 4;                // output pixels per lane
 constexpr int CL_WPX = 32 * CL_LPX;      // output pixels per warp and row
 template <int N> struct ClInt { static constexpr int value = N; };       // compile-time ring slot for the callers' unrolled bodies
+template <bool B> struct ClBool { static constexpr bool value = B; };    // checked / unchecked body
 
 // DIV: 0 acc >> shift | 1 umulhi(acc, magic) | 2 acc / norm (signed taps) | 3 byte 1 (norm 256, u8 out) | 4 byte 2 (norm 65536, u8 out)
 template <int K, bool OUT_U8, int DIV, bool VBOX>

@@ -131,7 +131,7 @@ bool launch_conv_sep(const uint8_t *in, size_t in_pitch, int rows, int cols, int
     const int ob = out_is_u8 ? 1 : 4;
     const int smem = p.stages * (int)p.stage_bytes + 16 * p.stages + 128 + p.nw * 2 * CS_WPX * 3 * ob;
     // bands: an even number of rows, sized so that the CTAs fill a whole number of waves of resident CTAs
-    const int occ = K <= 5 ? CS_MINB5 : 3;
+    const int occ = K <= 5 ? CS_MINB5 : CS_MINB9;
     const long long slots = (long long)sm_count * occ;
     int best_rows = rows, best_score = 1 << 30;
     for (int wv = 1; wv <= 64; ++wv) {

@@ -23,6 +23,9 @@ namespace ompimg {
 #ifndef CS_MINB5
 #define CS_MINB5 4                     // resident CTAs per SM the K <= 5 kernels are compiled for (K > 5: 3)
 #endif
+#ifndef CS_MINB9
+#define CS_MINB9 3
+#endif
 #ifndef CS_NWARPS
 #define CS_NWARPS 4
 #endif
@@ -66,7 +69,7 @@ __device__ __forceinline__ bool elect_one() {
 // DIV: 0 acc >> shift | 1 umulhi(acc, magic) | 2 acc / norm (signed) | 3 byte 1 (norm 256, u8 out) | 4 byte 2 (norm 65536, u8 out)
 // VBOX (DIV 0 or 1 only): see the header comment.
 template <int K, bool OUT_U8, int DIV, bool VBOX>
-__global__ void __launch_bounds__((CS_NW + 1) * 32, K <= 5 ? CS_MINB5 : 3) conv_sep_kernel(const __grid_constant__ ConvSepParams p) {
+__global__ void __launch_bounds__((CS_NW + 1) * 32, K <= 5 ? CS_MINB5 : CS_MINB9) conv_sep_kernel(const __grid_constant__ ConvSepParams p) {
     using Lane = ConvLane<K, OUT_U8, DIV, VBOX>;
     constexpr int NP = Lane::NP;                    // trips per unrolled body; pair-rows in the vertical window
     constexpr int NWRD = Lane::NWRD;                // 32-bit words that hold a lane's 4+K-1 input pixels
@@ -150,11 +153,13 @@ __global__ void __launch_bounds__((CS_NW + 1) * 32, K <= 5 ? CS_MINB5 : 3) conv_
 
     uint32_t so = 0, fb = full0, ph = 0;           // ring position of the unrolled body's first trip
     int t0 = 0;
-    // one trip (two input rows) at ring slot s of the unrolled body
-    auto trip = [&](auto s_c) __attribute__((always_inline)) {
+    // one trip (two input rows) at ring slot s of the unrolled body.  CHECKED: the trip may not exist, may not emit (priming), may hold
+    // one output row only, and the warp's output may need per-lane stores; the unchecked body has none of that code (conv_tma.cuh).
+    auto trip = [&](auto s_c, auto checked_c) __attribute__((always_inline)) {
         constexpr int s = decltype(s_c)::value;
+        constexpr bool CHECKED = decltype(checked_c)::value;
         const int t = t0 + s;
-        if (t >= ntrips) return;
+        if (CHECKED && t >= ntrips) return;
         mbar_wait(fb + 8 * s, ph);
         uint32_t w[2][NWRD];
 #pragma unroll
@@ -167,24 +172,31 @@ __global__ void __launch_bounds__((CS_NW + 1) * 32, K <= 5 ? CS_MINB5 : 3) conv_
         __syncwarp();                                  // also: every lane has read the previous trip's staging rows
         if (elect_one()) mbar_arrive(fb + 8 * s + eoff);   // both rows of the stage are in registers
 
-        const bool emit = t >= (K - 1) / 2;
-        const bool two = ro + 1 < yb;
-        L.template rows2<s>(w, p, emit, two, wide, lval, lane, stg, stg_rd, orow, p.out_pitch);
+        const bool emit = !CHECKED || t >= NP - 1;
+        const bool two = !CHECKED || ro + 1 < yb;
+        L.template rows2<s, !CHECKED>(w, p, emit, two, wide, lval, lane, stg, stg_rd, orow, p.out_pitch);
         if (emit) {
             orow += 2 * p.out_pitch;
             ro += 2;
         }
     };
-    for (; t0 < ntrips; t0 += NP) {
-        trip(ClInt<0>{});
-        if constexpr (NP > 1) trip(ClInt<1>{});
-        if constexpr (NP > 2) trip(ClInt<2>{});
-        if constexpr (NP > 3) trip(ClInt<3>{});
-        if constexpr (NP > 4) trip(ClInt<4>{});
+    auto block = [&](auto checked_c) __attribute__((always_inline)) {
+        trip(ClInt<0>{}, checked_c);
+        if constexpr (NP > 1) trip(ClInt<1>{}, checked_c);
+        if constexpr (NP > 2) trip(ClInt<2>{}, checked_c);
+        if constexpr (NP > 3) trip(ClInt<3>{}, checked_c);
+        if constexpr (NP > 4) trip(ClInt<4>{}, checked_c);
+        t0 += NP;
         so += NP * stage_bytes;
         fb += 8 * NP;
         if (so == ring_bytes) { so = 0; fb = full0; ph ^= 1; }
-    }
+    };
+    // block 0 primes the window; blocks whose trips all exist and all emit two rows run unchecked when the warp's output leaves as
+    // whole 16-byte pieces; the rest checked
+    const int tfull = ((yb - ya) >> 1) + NP - 1;   // trips [NP-1, tfull) emit two rows each
+    block(ClBool<true>{});
+    while (wide && t0 + NP <= tfull) block(ClBool<false>{});
+    while (t0 < ntrips) block(ClBool<true>{});
 }
 
 template <int K>

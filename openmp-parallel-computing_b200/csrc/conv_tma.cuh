@@ -84,7 +84,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
-template <bool B> struct CtBool { static constexpr bool value = B; };
 
 // DIV: 0 acc >> shift | 1 umulhi(acc, magic) | 3 byte 1 (norm 256, u8 out) | 4 byte 2 (norm 65536, u8 out); taps >= 0.
 // VBOX (DIV 0 or 1 only): constant vertical taps, running window sums.
@@ -190,9 +189,9 @@ __global__ void __launch_bounds__(CT_WARPS * 32, K <= 5 ? (VBOX ? CT_MINB_5BOX :
 
     // block 0 primes the window; blocks whose trips all exist and all emit two rows run unchecked; the rest checked
     const int tfull = (nout >> 1) + NP - 1;        // trips [NP-1, tfull) emit two rows each
-    block(CtBool<true>{});
-    while (wide && t0 + NP <= tfull) block(CtBool<false>{});      // ragged strips / unaligned output rows stay on the checked body
-    while (t0 < ntrips) block(CtBool<true>{});
+    block(ClBool<true>{});
+    while (wide && t0 + NP <= tfull) block(ClBool<false>{});      // ragged strips / unaligned output rows stay on the checked body
+    while (t0 < ntrips) block(ClBool<true>{});
 }
 
 template <int K>
