@@ -30,7 +30,11 @@ template <int N> struct ClInt { static constexpr int value = N; };       // comp
 template <bool B> struct ClBool { static constexpr bool value = B; };    // checked / unchecked body
 
 // DIV: 0 acc >> shift | 1 umulhi(acc, magic) | 2 acc / norm (signed taps) | 3 byte 1 (norm 256, u8 out) | 4 byte 2 (norm 65536, u8 out)
-template <int K, bool OUT_U8, int DIV, bool VBOX>
+// E1 (unsigned taps, !VBOX): u[0] == u[K-1] == v[0] == v[K-1] == 1 (binomial and other unit-ended taps).  A tap word of the horizontal pass
+// that holds a single tap, and the half pair-row at either end of the vertical window, then contribute the sample itself: one byte /
+// half-word extraction (ALU pipe) starts the accumulator instead of an IDP -- 1.5 of the 8 IDP per output byte at K = 9, on the pipe
+// that bounds that kernel.
+template <int K, bool OUT_U8, int DIV, bool VBOX, bool E1 = false>
 struct ConvLane {
     static constexpr bool SG = DIV == 2;
     static constexpr int NP = (K + 1) / 2;                 // calls per unrolled block; pair-rows in the vertical window
@@ -107,9 +111,20 @@ struct ConvLane {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     uint32_t acc = 0u;
+                    if (E1) {
 #pragma unroll
-                    for (int m = 0; m < NG; ++m)
-                        if (4 * m + 3 - i >= 0 && 4 * m - i < K) acc = dp4<SG>(X[ch][m], p.th[i][m < 3 ? m : 0], acc);
+                        for (int m = 0; m < NG; ++m) {          // words that hold exactly one tap (an end tap, = 1): add the sample byte
+                            const int first = 4 * m - i, last = 4 * m + 3 - i;
+                            const int lo = first < 0 ? 0 : first, hi = last > K - 1 ? K - 1 : last;
+                            if (hi == lo && hi >= 0 && lo <= K - 1) acc += (X[ch][m] >> (8 * (lo - first))) & 0xffu;
+                        }
+                    }
+#pragma unroll
+                    for (int m = 0; m < NG; ++m) {
+                        const int first = 4 * m - i, last = 4 * m + 3 - i;
+                        const int lo = first < 0 ? 0 : first, hi = last > K - 1 ? K - 1 : last;
+                        if (hi >= lo && !(E1 && hi == lo)) acc = dp4<SG>(X[ch][m], p.th[i][m < 3 ? m : 0], acc);
+                    }
                     h[rho][ch * 4 + i] = acc;
                 }
         }
@@ -154,8 +169,12 @@ struct ConvLane {
 #pragma unroll
                 for (int c = 0; c < 12; ++c) {
                     uint32_t acc = 0u;
+                    // E1: the newest pair-row holds only the window's last row for the first output row (tap u[K-1] = 1, low half),
+                    // the oldest only its first row for the second output row (tap u[0] = 1, high half)
+                    if (E1) acc = half ? W[((S + 1) % NP) * 12 + c] >> 16 : W[S * 12 + c] & 0xffffu;
 #pragma unroll
                     for (int k = 0; k < NP; ++k) {
+                        if (E1 && k == (half ? 0 : NP - 1)) continue;
                         const uint32_t wq = W[((S + 1 + k) % NP) * 12 + c];
                         acc = half ? dp2<SG, true>(wq, p.ut[k], acc) : dp2<SG, false>(wq, p.ut[k], acc);
                     }

@@ -71,7 +71,7 @@ struct ConvTmaParams {
 
 // band geometry and ring depth are chosen by the launcher from the kernel's occupancy (conv_sep.cu passes everything else)
 template <int K>
-cudaError_t launch_conv_tma_k(ConvTmaParams &p, int out_u8, int div, int vbox, int sm_count, cudaStream_t st);
+cudaError_t launch_conv_tma_k(ConvTmaParams &p, int out_u8, int div, int vbox, int ends1, int sm_count, cudaStream_t st);
 
 #ifdef OMPIMG_CONV_TMA_IMPL
 
@@ -87,9 +87,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
 
 // DIV: 0 acc >> shift | 1 umulhi(acc, magic) | 3 byte 1 (norm 256, u8 out) | 4 byte 2 (norm 65536, u8 out); taps >= 0.
 // VBOX (DIV 0 or 1 only): constant vertical taps, running window sums.
-template <int K, bool OUT_U8, int DIV, bool VBOX>
+template <int K, bool OUT_U8, int DIV, bool VBOX, bool E1 = false>
 __global__ void __launch_bounds__(CT_WARPS * 32, K <= 5 ? (VBOX ? CT_MINB_5BOX : CT_MINB_5GEN) : (VBOX ? CT_MINB_9BOX : CT_MINB_9GEN)) conv_tma_kernel(const __grid_constant__ ConvTmaParams p) {
-    using Lane = ConvLane<K, OUT_U8, DIV, VBOX>;
+    using Lane = ConvLane<K, OUT_U8, DIV, VBOX, E1>;
     constexpr int NP = Lane::NP;                    // trips per block; pair-rows in the vertical window
     constexpr int NWRD = Lane::NWRD;                // 32-bit words that hold a lane's 4+K-1 input pixels
     constexpr int OB = Lane::OB;
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(CT_WARPS * 32, K <= 5 ? (VBOX ? CT_MINB_5BOX :
 }
 
 template <int K>
-cudaError_t launch_conv_tma_k(ConvTmaParams &p, int out_u8, int div, int vbox, int sm_count, cudaStream_t st) {
+cudaError_t launch_conv_tma_k(ConvTmaParams &p, int out_u8, int div, int vbox, int ends1, int sm_count, cudaStream_t st) {
     auto go = [&](auto kern) -> cudaError_t {
         const int ob = out_u8 ? 1 : 4;
         static int stages_env = -1, band_env = -1, occ_env = -1;
@@ -242,6 +242,17 @@ cudaError_t launch_conv_tma_k(ConvTmaParams &p, int out_u8, int div, int vbox, i
         if (div == 0) return out_u8 ? go(conv_tma_kernel<K, true, 0, true>) : go(conv_tma_kernel<K, false, 0, true>);
         if (div == 1) return out_u8 ? go(conv_tma_kernel<K, true, 1, true>) : go(conv_tma_kernel<K, false, 1, true>);
         return cudaErrorInvalidValue;
+    }
+    if constexpr (K >= 7) {       // unit-ended taps (binomial ...): the variant with fewer IDP, where that pipe is the bound
+        if (ends1) {
+            switch (div) {
+                case 0: return out_u8 ? go(conv_tma_kernel<K, true, 0, false, true>) : go(conv_tma_kernel<K, false, 0, false, true>);
+                case 1: return out_u8 ? go(conv_tma_kernel<K, true, 1, false, true>) : go(conv_tma_kernel<K, false, 1, false, true>);
+                case 3: if (out_u8) return go(conv_tma_kernel<K, true, 3, false, true>); break;
+                case 4: if (out_u8) return go(conv_tma_kernel<K, true, 4, false, true>); break;
+            }
+            return cudaErrorInvalidValue;
+        }
     }
     switch (div) {
         case 0: return out_u8 ? go(conv_tma_kernel<K, true, 0, false>) : go(conv_tma_kernel<K, false, 0, false>);

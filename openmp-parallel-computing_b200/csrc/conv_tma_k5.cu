@@ -5,5 +5,5 @@
 #include "conv_tma.cuh"
 
 namespace ompimg {
-template cudaError_t launch_conv_tma_k<5>(ConvTmaParams &, int, int, int, int, cudaStream_t);
+template cudaError_t launch_conv_tma_k<5>(ConvTmaParams &, int, int, int, int, int, cudaStream_t);
 }
