@@ -30,7 +30,7 @@ template <int N> struct ClInt { static constexpr int value = N; };       // comp
 template <bool B> struct ClBool { static constexpr bool value = B; };    // checked / unchecked body
 
 // DIV: 0 acc >> shift | 1 umulhi(acc, magic) | 2 acc / norm (signed taps) | 3 byte 1 (norm 256, u8 out) | 4 byte 2 (norm 65536, u8 out)
-// E1 (unsigned taps, !VBOX): u[0] == u[K-1] == v[0] == v[K-1] == 1 (binomial and other unit-ended taps).  A tap word of the horizontal pass
+// E1 (unsigned taps): v[0] == v[K-1] == 1 and, unless VBOX, u[0] == u[K-1] == 1 (binomial and other unit-ended taps, the plain box).  A tap word of the horizontal pass
 // that holds a single tap, and the half pair-row at either end of the vertical window, then contribute the sample itself: one byte /
 // half-word extraction (ALU pipe) starts the accumulator instead of an IDP -- 1.5 of the 8 IDP per output byte at K = 9, on the pipe
 // that bounds that kernel.

@@ -99,7 +99,7 @@ bool launch_conv_sep(const uint8_t *in, size_t in_pitch, int rows, int cols, int
                 // unit-ended unsigned taps (binomial ...): see ConvLane's E1
                 static int e1_env = -1;
                 if (e1_env < 0) { const char *e = getenv("OMPIMG_CONV_E1"); e1_env = e ? atoi(e) : 1; }
-                const int ends1 = e1_env && !vbox && div != 2 && nonneg && u[0] == 1 && u[K - 1] == 1 && vv[0] == 1 && vv[K - 1] == 1;
+                const int ends1 = e1_env && div != 2 && nonneg && vv[0] == 1 && vv[K - 1] == 1 && (vbox || (u[0] == 1 && u[K - 1] == 1));
                 switch (K) {
                     case 3: *err = launch_conv_tma_k<3>(q, out_is_u8, div, vbox, ends1, sm_count, st); break;
                     case 5: *err = launch_conv_tma_k<5>(q, out_is_u8, div, vbox, ends1, sm_count, st); break;

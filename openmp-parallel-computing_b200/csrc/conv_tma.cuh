@@ -45,6 +45,9 @@ namespace ompimg {
 #ifndef CT_MINB_9GEN
 #define CT_MINB_9GEN 3
 #endif
+#ifndef CT_E1_MIN_K
+#define CT_E1_MIN_K 3                     // smallest K that gets the unit-ended-taps variant (5x5 binomial 824 -> 898 Gpx/s, 9x9 591 -> 674)
+#endif
 constexpr int CT_WARPS = 4;              // warps (tasks) per CTA
 constexpr int CT_LPX = CL_LPX;           // output pixels per lane
 constexpr int CT_WPX = CL_WPX;           // output pixels per warp and row
@@ -239,11 +242,18 @@ cudaError_t launch_conv_tma_k(ConvTmaParams &p, int out_u8, int div, int vbox, i
         return cudaGetLastError();
     };
     if (vbox) {
+        if constexpr (K >= CT_E1_MIN_K) {
+            if (ends1) {          // plain box: the horizontal pass's single-tap words by extraction
+                if (div == 0) return out_u8 ? go(conv_tma_kernel<K, true, 0, true, true>) : go(conv_tma_kernel<K, false, 0, true, true>);
+                if (div == 1) return out_u8 ? go(conv_tma_kernel<K, true, 1, true, true>) : go(conv_tma_kernel<K, false, 1, true, true>);
+                return cudaErrorInvalidValue;
+            }
+        }
         if (div == 0) return out_u8 ? go(conv_tma_kernel<K, true, 0, true>) : go(conv_tma_kernel<K, false, 0, true>);
         if (div == 1) return out_u8 ? go(conv_tma_kernel<K, true, 1, true>) : go(conv_tma_kernel<K, false, 1, true>);
         return cudaErrorInvalidValue;
     }
-    if constexpr (K >= 7) {       // unit-ended taps (binomial ...): the variant with fewer IDP, where that pipe is the bound
+    if constexpr (K >= CT_E1_MIN_K) {       // unit-ended taps (binomial ...): the variant with fewer IDP, where that pipe is the bound
         if (ends1) {
             switch (div) {
                 case 0: return out_u8 ? go(conv_tma_kernel<K, true, 0, false, true>) : go(conv_tma_kernel<K, false, 0, false, true>);
