@@ -1,7 +1,7 @@
 // conv_sep.cuh -- K x K convolution with rank-1 taps (box, binomial/Gaussian, ...) on interleaved
 // uint8 RGB: the fast path of a6 (old/parallel_convolution.c:8-24).  Same results as conv.cu's
 // kernels: out[r][c][p] = (sum_{kr,kc} in[r+kr][c+kc][p] * u[kr]*v[kc]) / norm, C division, no clamp,
-// pre-padded top-left anchored input.  One translation unit per K (conv_sep_k*.cu) instantiates it.
+// pre-padded top-left anchored input.  Instantiated by conv_sep_inst.cu, once per K and group of variants.
 //
 // Data movement: a CTA owns a band of output rows x a strip of NW*128 pixels.  A producer warp
 // streams the band's input rows (two per stage) into a shared-memory ring with 1-D bulk asynchronous
@@ -51,8 +51,15 @@ struct ConvSepParams {
     int32_t shift, norm;
 };
 
+// The kernel variants of one K are instantiated in four translation units (conv_sep_inst.cu compiled once per K and PART, so that they
+// build in parallel): PART 0 / 1 constant vertical taps with int32 / uint8 output, 2 / 3 general taps with int32 / uint8 output.
+template <int K, int PART>
+cudaError_t launch_conv_sep_part(const ConvSepParams &p, int div, dim3 grid, int smem, cudaStream_t st);
 template <int K>
-cudaError_t launch_conv_sep_k(const ConvSepParams &p, int out_u8, int div, int vbox, dim3 grid, int smem, cudaStream_t st);
+inline cudaError_t launch_conv_sep_k(const ConvSepParams &p, int out_u8, int div, int vbox, dim3 grid, int smem, cudaStream_t st) {
+    if (vbox) return out_u8 ? launch_conv_sep_part<K, 1>(p, div, grid, smem, st) : launch_conv_sep_part<K, 0>(p, div, grid, smem, st);
+    return out_u8 ? launch_conv_sep_part<K, 3>(p, div, grid, smem, st) : launch_conv_sep_part<K, 2>(p, div, grid, smem, st);
+}
 
 #ifdef OMPIMG_CONV_SEP_IMPL
 
@@ -199,8 +206,8 @@ __global__ void __launch_bounds__((CS_NW + 1) * 32, K <= 5 ? CS_MINB5 : CS_MINB9
     while (t0 < ntrips) block(ClBool<true>{});
 }
 
-template <int K>
-cudaError_t launch_conv_sep_k(const ConvSepParams &p, int out_u8, int div, int vbox, dim3 grid, int smem, cudaStream_t st) {
+template <int K, int PART>
+cudaError_t launch_conv_sep_part(const ConvSepParams &p, int div, dim3 grid, int smem, cudaStream_t st) {
     auto go = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
@@ -208,19 +215,21 @@ cudaError_t launch_conv_sep_k(const ConvSepParams &p, int out_u8, int div, int v
         kern<<<grid, (p.nw + 1) * 32, smem, st>>>(p);
         return cudaGetLastError();
     };
-    if (vbox) {
-        if (div == 0) return out_u8 ? go(conv_sep_kernel<K, true, 0, true>) : go(conv_sep_kernel<K, false, 0, true>);
-        if (div == 1) return out_u8 ? go(conv_sep_kernel<K, true, 1, true>) : go(conv_sep_kernel<K, false, 1, true>);
+    constexpr bool U8 = (PART & 1) != 0;
+    if constexpr (PART < 2) {             // constant vertical taps
+        if (div == 0) return go(conv_sep_kernel<K, U8, 0, true>);
+        if (div == 1) return go(conv_sep_kernel<K, U8, 1, true>);
+        return cudaErrorInvalidValue;
+    } else {
+        switch (div) {
+            case 0: return go(conv_sep_kernel<K, U8, 0, false>);
+            case 1: return go(conv_sep_kernel<K, U8, 1, false>);
+            case 2: return go(conv_sep_kernel<K, U8, 2, false>);
+            case 3: if constexpr (U8) return go(conv_sep_kernel<K, true, 3, false>); break;
+            case 4: if constexpr (U8) return go(conv_sep_kernel<K, true, 4, false>); break;
+        }
         return cudaErrorInvalidValue;
     }
-    switch (div) {
-        case 0: return out_u8 ? go(conv_sep_kernel<K, true, 0, false>) : go(conv_sep_kernel<K, false, 0, false>);
-        case 1: return out_u8 ? go(conv_sep_kernel<K, true, 1, false>) : go(conv_sep_kernel<K, false, 1, false>);
-        case 2: return out_u8 ? go(conv_sep_kernel<K, true, 2, false>) : go(conv_sep_kernel<K, false, 2, false>);
-        case 3: if (out_u8) return go(conv_sep_kernel<K, true, 3, false>); break;
-        case 4: if (out_u8) return go(conv_sep_kernel<K, true, 4, false>); break;
-    }
-    return cudaErrorInvalidValue;
 }
 
 #endif  // OMPIMG_CONV_SEP_IMPL

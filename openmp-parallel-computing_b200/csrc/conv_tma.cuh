@@ -2,7 +2,7 @@
 // the fast path of a6 (old/parallel_convolution.c:8-24) for inputs whose base and pitch are 16-byte
 // aligned (every device copy the host entry points make; conv_sep.cuh keeps the dense-pitch layouts).
 // Same results as conv.cu / conv_sep.cuh: out[r][c][p] = (sum_{kr,kc} in[r+kr][c+kc][p] * u[kr]*v[kc]) / norm,
-// C division, no clamp, pre-padded top-left anchored input.  One translation unit per K (conv_tma_k*.cu).
+// C division, no clamp, pre-padded top-left anchored input.  Instantiated by conv_tma_inst.cu, once per K and group of variants.
 //
 // Data movement.  Every WARP is its own pipeline (as in stencil.cu): it owns a band of output rows x a
 // strip of 128 pixels, runs a private ring of two-row stages with one mbarrier per stage, and an elected
@@ -72,9 +72,18 @@ struct ConvTmaParams {
     int32_t norm;                // unused here (signed taps take conv_sep.cuh); read by the shared lane code's DIV 2 branch only
 };
 
-// band geometry and ring depth are chosen by the launcher from the kernel's occupancy (conv_sep.cu passes everything else)
+// band geometry and ring depth are chosen by the launcher from the kernel's occupancy (conv_sep.cu passes everything else).
+// The kernel variants of one K are instantiated in four translation units (conv_tma_inst.cu compiled once per K and PART, so that
+// they build in parallel): PART 0 constant vertical taps (box), 1 the same with unit-ended horizontal taps, 2 general taps, 3 general
+// unit-ended taps.
+template <int K, int PART>
+cudaError_t launch_conv_tma_part(ConvTmaParams &p, int out_u8, int div, int sm_count, cudaStream_t st);
 template <int K>
-cudaError_t launch_conv_tma_k(ConvTmaParams &p, int out_u8, int div, int vbox, int ends1, int sm_count, cudaStream_t st);
+inline cudaError_t launch_conv_tma_k(ConvTmaParams &p, int out_u8, int div, int vbox, int ends1, int sm_count, cudaStream_t st) {
+    const bool e1 = ends1 && K >= CT_E1_MIN_K;
+    if (vbox) return e1 ? launch_conv_tma_part<K, 1>(p, out_u8, div, sm_count, st) : launch_conv_tma_part<K, 0>(p, out_u8, div, sm_count, st);
+    return e1 ? launch_conv_tma_part<K, 3>(p, out_u8, div, sm_count, st) : launch_conv_tma_part<K, 2>(p, out_u8, div, sm_count, st);
+}
 
 #ifdef OMPIMG_CONV_TMA_IMPL
 
@@ -197,8 +206,8 @@ __global__ void __launch_bounds__(CT_WARPS * 32, K <= 5 ? (VBOX ? CT_MINB_5BOX :
     while (t0 < ntrips) block(ClBool<true>{});
 }
 
-template <int K>
-cudaError_t launch_conv_tma_k(ConvTmaParams &p, int out_u8, int div, int vbox, int ends1, int sm_count, cudaStream_t st) {
+template <int K, int PART>
+cudaError_t launch_conv_tma_part(ConvTmaParams &p, int out_u8, int div, int sm_count, cudaStream_t st) {
     auto go = [&](auto kern) -> cudaError_t {
         const int ob = out_u8 ? 1 : 4;
         static int stages_env = -1, band_env = -1, occ_env = -1;
@@ -241,36 +250,21 @@ cudaError_t launch_conv_tma_k(ConvTmaParams &p, int out_u8, int div, int vbox, i
         kern<<<(unsigned)ctas, CT_WARPS * 32, smem, st>>>(p);
         return cudaGetLastError();
     };
-    if (vbox) {
-        if constexpr (K >= CT_E1_MIN_K) {
-            if (ends1) {          // plain box: the horizontal pass's single-tap words by extraction
-                if (div == 0) return out_u8 ? go(conv_tma_kernel<K, true, 0, true, true>) : go(conv_tma_kernel<K, false, 0, true, true>);
-                if (div == 1) return out_u8 ? go(conv_tma_kernel<K, true, 1, true, true>) : go(conv_tma_kernel<K, false, 1, true, true>);
-                return cudaErrorInvalidValue;
-            }
+    constexpr bool VB = PART < 2, E1 = (PART & 1) != 0;
+    if constexpr (E1 && K < CT_E1_MIN_K) return cudaErrorInvalidValue;
+    else if constexpr (VB) {
+        if (div == 0) return out_u8 ? go(conv_tma_kernel<K, true, 0, true, E1>) : go(conv_tma_kernel<K, false, 0, true, E1>);
+        if (div == 1) return out_u8 ? go(conv_tma_kernel<K, true, 1, true, E1>) : go(conv_tma_kernel<K, false, 1, true, E1>);
+        return cudaErrorInvalidValue;
+    } else {
+        switch (div) {
+            case 0: return out_u8 ? go(conv_tma_kernel<K, true, 0, false, E1>) : go(conv_tma_kernel<K, false, 0, false, E1>);
+            case 1: return out_u8 ? go(conv_tma_kernel<K, true, 1, false, E1>) : go(conv_tma_kernel<K, false, 1, false, E1>);
+            case 3: if (out_u8) return go(conv_tma_kernel<K, true, 3, false, E1>); break;
+            case 4: if (out_u8) return go(conv_tma_kernel<K, true, 4, false, E1>); break;
         }
-        if (div == 0) return out_u8 ? go(conv_tma_kernel<K, true, 0, true>) : go(conv_tma_kernel<K, false, 0, true>);
-        if (div == 1) return out_u8 ? go(conv_tma_kernel<K, true, 1, true>) : go(conv_tma_kernel<K, false, 1, true>);
         return cudaErrorInvalidValue;
     }
-    if constexpr (K >= CT_E1_MIN_K) {       // unit-ended taps (binomial ...): the variant with fewer IDP, where that pipe is the bound
-        if (ends1) {
-            switch (div) {
-                case 0: return out_u8 ? go(conv_tma_kernel<K, true, 0, false, true>) : go(conv_tma_kernel<K, false, 0, false, true>);
-                case 1: return out_u8 ? go(conv_tma_kernel<K, true, 1, false, true>) : go(conv_tma_kernel<K, false, 1, false, true>);
-                case 3: if (out_u8) return go(conv_tma_kernel<K, true, 3, false, true>); break;
-                case 4: if (out_u8) return go(conv_tma_kernel<K, true, 4, false, true>); break;
-            }
-            return cudaErrorInvalidValue;
-        }
-    }
-    switch (div) {
-        case 0: return out_u8 ? go(conv_tma_kernel<K, true, 0, false>) : go(conv_tma_kernel<K, false, 0, false>);
-        case 1: return out_u8 ? go(conv_tma_kernel<K, true, 1, false>) : go(conv_tma_kernel<K, false, 1, false>);
-        case 3: if (out_u8) return go(conv_tma_kernel<K, true, 3, false>); break;
-        case 4: if (out_u8) return go(conv_tma_kernel<K, true, 4, false>); break;
-    }
-    return cudaErrorInvalidValue;
 }
 
 #endif  // OMPIMG_CONV_TMA_IMPL
