@@ -77,6 +77,11 @@ bool launch_conv_sep(const uint8_t *in, size_t in_pitch, int rows, int cols, int
     auto ub = [&](int k) -> uint32_t { return k >= 0 && k < K ? (uint32_t)(u[k] & 255) : 0u; };
     for (int q = 0; q < 5; ++q) ut[q] = ub(2 * q) | ub(2 * q + 1) << 8 | ub(2 * q - 1) << 16 | ub(2 * q) << 24;
 
+    // unit-ended unsigned taps (every binomial, the plain box): the kernel variants with fewer IDP (ConvLane's E1)
+    static int e1_env = -1;
+    if (e1_env < 0) { const char *e = getenv("OMPIMG_CONV_E1"); e1_env = e ? atoi(e) : 1; }
+    const int ends1 = e1_env && div != 2 && nonneg && vv[0] == 1 && vv[K - 1] == 1 && (vbox || (u[0] == 1 && u[K - 1] == 1));
+
     // ---- 16-byte aligned base and pitch, unsigned taps: the warp-autonomous kernel fed by tensor-map copies (conv_tma.cuh)
     static int tma_env = -1;
     if (tma_env < 0) { const char *e = getenv("OMPIMG_CONV_TMA"); tma_env = e ? atoi(e) : 1; }
@@ -96,10 +101,6 @@ bool launch_conv_sep(const uint8_t *in, size_t in_pitch, int rows, int cols, int
                 for (int i = 0; i < 4; ++i) for (int m = 0; m < 3; ++m) q.th[i][m] = th[i][m];
                 for (int k = 0; k < 5; ++k) q.ut[k] = ut[k];
                 q.magic = magic; q.shift = shift;
-                // unit-ended unsigned taps (binomial ...): see ConvLane's E1
-                static int e1_env = -1;
-                if (e1_env < 0) { const char *e = getenv("OMPIMG_CONV_E1"); e1_env = e ? atoi(e) : 1; }
-                const int ends1 = e1_env && div != 2 && nonneg && vv[0] == 1 && vv[K - 1] == 1 && (vbox || (u[0] == 1 && u[K - 1] == 1));
                 switch (K) {
                     case 3: *err = launch_conv_tma_k<3>(q, out_is_u8, div, vbox, ends1, sm_count, st); break;
                     case 5: *err = launch_conv_tma_k<5>(q, out_is_u8, div, vbox, ends1, sm_count, st); break;
@@ -153,10 +154,10 @@ bool launch_conv_sep(const uint8_t *in, size_t in_pitch, int rows, int cols, int
     const int nbands = (rows + p.band_rows - 1) / p.band_rows;
     const dim3 grid((unsigned)nbands, (unsigned)nstrips);
     switch (K) {
-        case 3: *err = launch_conv_sep_k<3>(p, out_is_u8, div, vbox, grid, smem, st); break;
-        case 5: *err = launch_conv_sep_k<5>(p, out_is_u8, div, vbox, grid, smem, st); break;
-        case 7: *err = launch_conv_sep_k<7>(p, out_is_u8, div, vbox, grid, smem, st); break;
-        default: *err = launch_conv_sep_k<9>(p, out_is_u8, div, vbox, grid, smem, st); break;
+        case 3: *err = launch_conv_sep_k<3>(p, out_is_u8, div, vbox, ends1, grid, smem, st); break;
+        case 5: *err = launch_conv_sep_k<5>(p, out_is_u8, div, vbox, ends1, grid, smem, st); break;
+        case 7: *err = launch_conv_sep_k<7>(p, out_is_u8, div, vbox, ends1, grid, smem, st); break;
+        default: *err = launch_conv_sep_k<9>(p, out_is_u8, div, vbox, ends1, grid, smem, st); break;
     }
     return true;
 }

@@ -51,12 +51,17 @@ struct ConvSepParams {
     int32_t shift, norm;
 };
 
-// The kernel variants of one K are instantiated in four translation units (conv_sep_inst.cu compiled once per K and PART, so that they
-// build in parallel): PART 0 / 1 constant vertical taps with int32 / uint8 output, 2 / 3 general taps with int32 / uint8 output.
+// The kernel variants of one K are instantiated in eight translation units (conv_sep_inst.cu compiled once per K and PART, so that they
+// build in parallel): PART 0 / 1 constant vertical taps with int32 / uint8 output, 2 / 3 general taps with int32 / uint8 output, 4..7 the
+// same four for unit-ended taps (ConvLane's E1).
 template <int K, int PART>
 cudaError_t launch_conv_sep_part(const ConvSepParams &p, int div, dim3 grid, int smem, cudaStream_t st);
 template <int K>
-inline cudaError_t launch_conv_sep_k(const ConvSepParams &p, int out_u8, int div, int vbox, dim3 grid, int smem, cudaStream_t st) {
+inline cudaError_t launch_conv_sep_k(const ConvSepParams &p, int out_u8, int div, int vbox, int ends1, dim3 grid, int smem, cudaStream_t st) {
+    if (ends1 && div != 2) {
+        if (vbox) return out_u8 ? launch_conv_sep_part<K, 5>(p, div, grid, smem, st) : launch_conv_sep_part<K, 4>(p, div, grid, smem, st);
+        return out_u8 ? launch_conv_sep_part<K, 7>(p, div, grid, smem, st) : launch_conv_sep_part<K, 6>(p, div, grid, smem, st);
+    }
     if (vbox) return out_u8 ? launch_conv_sep_part<K, 1>(p, div, grid, smem, st) : launch_conv_sep_part<K, 0>(p, div, grid, smem, st);
     return out_u8 ? launch_conv_sep_part<K, 3>(p, div, grid, smem, st) : launch_conv_sep_part<K, 2>(p, div, grid, smem, st);
 }
@@ -75,9 +80,9 @@ __device__ __forceinline__ bool elect_one() {
 }
 // DIV: 0 acc >> shift | 1 umulhi(acc, magic) | 2 acc / norm (signed) | 3 byte 1 (norm 256, u8 out) | 4 byte 2 (norm 65536, u8 out)
 // VBOX (DIV 0 or 1 only): see the header comment.
-template <int K, bool OUT_U8, int DIV, bool VBOX>
+template <int K, bool OUT_U8, int DIV, bool VBOX, bool E1 = false>
 __global__ void __launch_bounds__((CS_NW + 1) * 32, K <= 5 ? CS_MINB5 : CS_MINB9) conv_sep_kernel(const __grid_constant__ ConvSepParams p) {
-    using Lane = ConvLane<K, OUT_U8, DIV, VBOX>;
+    using Lane = ConvLane<K, OUT_U8, DIV, VBOX, E1>;
     constexpr int NP = Lane::NP;                    // trips per unrolled body; pair-rows in the vertical window
     constexpr int NWRD = Lane::NWRD;                // 32-bit words that hold a lane's 4+K-1 input pixels
     constexpr int OB = Lane::OB;
@@ -215,18 +220,18 @@ cudaError_t launch_conv_sep_part(const ConvSepParams &p, int div, dim3 grid, int
         kern<<<grid, (p.nw + 1) * 32, smem, st>>>(p);
         return cudaGetLastError();
     };
-    constexpr bool U8 = (PART & 1) != 0;
-    if constexpr (PART < 2) {             // constant vertical taps
-        if (div == 0) return go(conv_sep_kernel<K, U8, 0, true>);
-        if (div == 1) return go(conv_sep_kernel<K, U8, 1, true>);
+    constexpr bool U8 = (PART & 1) != 0, VB = (PART & 2) == 0, E1 = PART >= 4;        // PART 4..7: unit-ended taps (ConvLane's E1), unsigned only
+    if constexpr (VB) {                   // constant vertical taps
+        if (div == 0) return go(conv_sep_kernel<K, U8, 0, true, E1>);
+        if (div == 1) return go(conv_sep_kernel<K, U8, 1, true, E1>);
         return cudaErrorInvalidValue;
     } else {
         switch (div) {
-            case 0: return go(conv_sep_kernel<K, U8, 0, false>);
-            case 1: return go(conv_sep_kernel<K, U8, 1, false>);
-            case 2: return go(conv_sep_kernel<K, U8, 2, false>);
-            case 3: if constexpr (U8) return go(conv_sep_kernel<K, true, 3, false>); break;
-            case 4: if constexpr (U8) return go(conv_sep_kernel<K, true, 4, false>); break;
+            case 0: return go(conv_sep_kernel<K, U8, 0, false, E1>);
+            case 1: return go(conv_sep_kernel<K, U8, 1, false, E1>);
+            case 2: if constexpr (!E1) return go(conv_sep_kernel<K, U8, 2, false>); break;
+            case 3: if constexpr (U8) return go(conv_sep_kernel<K, true, 3, false, E1>); break;
+            case 4: if constexpr (U8) return go(conv_sep_kernel<K, true, 4, false, E1>); break;
         }
         return cudaErrorInvalidValue;
     }

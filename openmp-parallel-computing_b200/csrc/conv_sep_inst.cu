@@ -1,5 +1,5 @@
 // conv_sep_inst.cu -- explicit instantiation of one group of conv_sep.cuh's kernel variants: compiled once per
-// (CS_INST_K in 3 5 7 9) x (CS_INST_PART in 0..3) by the Makefile, so that the sixteen groups build in parallel.
+// (CS_INST_K in 3 5 7 9) x (CS_INST_PART in 0..7) by the Makefile, so that the groups build in parallel.
 #ifndef CS_INST_K
 #define CS_INST_K 3      // a bare `nvcc -c` of this file builds the smallest group
 #define CS_INST_PART 0
