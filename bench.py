@@ -779,6 +779,21 @@ def other_kernels(pkg, L, peak, with_cpu=True):
     # cfg4: 8192x8192 RGB box / binomial blur (uint8 out).  Device layout: rows 128-byte aligned like every device copy the host entry
     # points make (conv_tma.cuh: tensor-map copies); the reference's dense (cols+K-1)*3 pitch (conv_sep.cuh) is timed beside it.
     rows = cols = 8192
+    gold = {}
+    gp = ROOT / "tests" / "golden" / "conv_cfg4.json"          # output byte sums from the CPU oracle (tools/make_conv_checksums.py)
+    if gp.exists():
+        gold = json.loads(gp.read_text()).get("sums", {})
+    csum = pkg.DeviceBuffer(64)
+
+    def conv_check(which):
+        """sum of the output bytes of the last launch against the oracle's constant for this kernel and layout (None without one)"""
+        if which not in gold:
+            return None
+        csum.fill(0)
+        ck(pkg, L.ompimg_byte_sum_dev(dst.ptr, cols * 3, cols * 3, rows, csum.ptr, 0), "byte_sum")
+        pkg.sync()
+        return int(np.frombuffer(csum.download(8).tobytes(), np.uint64)[0]) == gold[which]["out_byte_sum"]
+
     for K in (5, 9):
         pr, pc = rows + K - 1, cols + K - 1
         ip = (pc * 3 + 127) // 128 * 128
@@ -793,10 +808,13 @@ def other_kernels(pkg, L, peak, with_cpu=True):
             key = f"conv_{name}{K}x{K}_8192x8192"
             out[key] = entry(rows * cols, 6, timeit(lambda: L.ompimg_conv_u8_dev(src.ptr, ip, rows, cols, K, tp.ctypes.data, nm, dst.ptr, cols * 3, 0), 10))
             out[key]["in_pitch"] = ip
+            out[key]["equals_oracle"] = conv_check(f"{name}{K}x{K}_aligned128")
             out[key]["dense_pitch"] = entry(rows * cols, 6, timeit(lambda: L.ompimg_conv_u8_dev(src.ptr, pc * 3, rows, cols, K, tp.ctypes.data, nm, dst.ptr, cols * 3, 0), 10))
             out[key]["dense_pitch"]["in_pitch"] = pc * 3
+            out[key]["dense_pitch"]["equals_oracle"] = conv_check(f"{name}{K}x{K}_dense")
         out[f"conv_box{K}x{K}_8192x8192"]["cpu"] = partner("conv", sorted({1, cores}), K=K)
         src.free(); dst.free()
+    csum.free()
     # a7: channel sums, 8192x8192
     src = pkg.DeviceBuffer(rows * cols * 3); sums = pkg.DeviceBuffer(64)
     pkg.synth_dev(src, src.nbytes, 5); sums.fill(0)
