@@ -737,6 +737,18 @@ def other_kernels(pkg, L, peak, with_cpu=True):
             res[f"threads_{th}"] = d
         return res
 
+    # frame-level parity inside the bench: the first and last frame of each batch against the CPU oracle on the same synthetic bytes
+    # (the oracle is the checker here, as in the cpu_baseline leg; full-size and edge-case parity is tests/)
+    O = None
+    if with_cpu:
+        try:
+            O = _oracle()
+        except Exception:
+            O = None
+
+    def same(got, want):
+        return bool(np.array_equal(np.asarray(got).reshape(-1), np.asarray(want).reshape(-1)))
+
     n = 128
     # cfg1 shape: in-place grayscale, 1920x1080 RGB x 512 frames (3.2 GB)
     n1, w1, h1 = 512, 1920, 1080
@@ -744,12 +756,28 @@ def other_kernels(pkg, L, peak, with_cpu=True):
     pkg.synth_dev(b, b.nbytes, 1)
     out["gray_inplace_1920x1080x512"] = entry(n1 * w1 * h1, 6, timeit(lambda: L.ompimg_gray_inplace_dev(b.ptr, w1 * 3, w1, h1, 3, n1, w1 * h1 * 3, 0)))
     out["gray_inplace_1920x1080x512"]["cpu"] = partner("gray", sorted({1, 2, 4, 6, cores}))
+    fb1 = w1 * h1 * 3
+    gray_ref = {}
+    if O:
+        ok = True
+        for f in (0, n1 - 1):                        # 13 in-place applications so far (3 warm-up + 10 timed)
+            ref = O.synth(fb1, 1, f * fb1)
+            for _ in range(13):
+                O.gray_inplace(ref, 3)
+            gray_ref[f] = ref
+            ok = ok and same(b.download(fb1, offset=f * fb1), ref)
+        out["gray_inplace_1920x1080x512"]["equals_oracle"] = ok
     # RGB -> packed luma plane (north star (2): 3 B read + 1 B written per pixel), same frames
     lum = pkg.DeviceBuffer(n1 * w1 * h1)
     out["rgb_to_luma_1920x1080x512"] = entry(n1 * w1 * h1, 4, timeit(lambda: L.ompimg_rgb_to_luma_dev(b.ptr, w1 * 3, 3, lum.ptr, w1, w1, h1, n1, w1 * h1 * 3, w1 * h1, 0)))
     # a8: legacy (r+g+b)/3 grayscale with min/max, one 1920 x (1080*512) image
     mm = pkg.DeviceBuffer(64); g3 = pkg.DeviceBuffer(n1 * w1 * h1 * 3)
     out["gray_avg3_minmax_1920x552960"] = entry(n1 * w1 * h1, 6, timeit(lambda: L.ompimg_gray_avg3_dev(b.ptr, w1 * 3, g3.ptr, w1 * 3, h1 * n1, w1, mm.ptr, 0)))
+    if O:
+        f = n1 - 1
+        img_f = gray_ref[f].reshape(h1, w1, 3)
+        out["rgb_to_luma_1920x1080x512"]["equals_oracle"] = same(lum.download(w1 * h1, offset=f * w1 * h1), O.rgb_to_luma(img_f))
+        out["gray_avg3_minmax_1920x552960"]["equals_oracle"] = same(g3.download(fb1, offset=f * fb1), O.gray_avg3_u8(img_f)[0])
     lum.free(); mm.free(); g3.free()
     b.free()
     # cfg2 shape: Sobel plane->plane, 2000x3000 (pitch 2048) x 128 planes
@@ -758,10 +786,22 @@ def other_kernels(pkg, L, peak, with_cpu=True):
     pkg.synth_dev(s, s.nbytes, 2); d.fill(0)
     out["sobel_plane_2000x3000x128"] = entry(n * w2 * h2, 2, timeit(lambda: L.ompimg_sobel_dev(s.ptr, p2, d.ptr, p2, w2, h2, n, p2 * h2, p2 * h2, 0)))
     out["sobel_plane_2000x3000x128"]["cpu"] = partner("sobel", sorted({1, cores}))
+    if O:
+        ok = True
+        for f in (0, n - 1):
+            src_f = O.synth(p2 * h2, 2, f * p2 * h2).reshape(h2, p2)[:, :w2]
+            got = d.download(p2 * h2, offset=f * p2 * h2).reshape(h2, p2)[:, :w2]
+            ok = ok and same(got, O.sobel(np.ascontiguousarray(src_f)))          # dst was zeroed: the untouched border is zero on both sides
+        out["sobel_plane_2000x3000x128"]["equals_oracle"] = ok
     # same kernel on 3840x2160 planes
     w3, h3 = 3840, 2160
     n3 = min(n, s.nbytes // (w3 * h3))
+    d.fill(0)
     out[f"sobel_plane_3840x2160x{n3}"] = entry(n3 * w3 * h3, 2, timeit(lambda: L.ompimg_sobel_dev(s.ptr, w3, d.ptr, w3, w3, h3, n3, w3 * h3, w3 * h3, 0)))
+    if O:
+        f = n3 - 1
+        src_f = O.synth(w3 * h3, 2, f * w3 * h3).reshape(h3, w3)
+        out[f"sobel_plane_3840x2160x{n3}"]["equals_oracle"] = same(d.download(w3 * h3, offset=f * w3 * h3), O.sobel(src_f))
     s.free(); d.free()
     # a5 semantics: RGB in place -> RGB edge, 3840x2160 x 64, the driver's loop of 10 passes per call (main_with_sobel.c:51-74 x passes):
     # one preparation kernel per call, then one fused launch per pass (each pass writes the next one's seam data)
@@ -775,6 +815,13 @@ def other_kernels(pkg, L, peak, with_cpu=True):
     out["gray_sobel_pass_rgb_inplace_3840x2160x64"]["passes_per_call"] = npass
     sec1 = timeit(lambda: L.ompimg_gray_sobel_pass_dev(img.ptr, W * 3, 3, e.ptr, W, W, H, n5, PX * 3, PX, 0))
     out["gray_sobel_pass_rgb_inplace_3840x2160x64"]["single_pass_call"] = entry(n5 * PX, 6, sec1)
+    if O:
+        f = n5 - 1                                   # 6 calls x 10 passes + 13 single-pass calls on the same image
+        ref = O.synth(PX * 3, 3, f * PX * 3).reshape(H, W, 3)
+        edge_ref = np.zeros((H, W), np.uint8)
+        for _ in range(6 * npass + 13):
+            ref, edge_ref = O.gray_sobel_pass(ref, edge_ref)
+        out["gray_sobel_pass_rgb_inplace_3840x2160x64"]["equals_oracle"] = same(img.download(PX * 3, offset=f * PX * 3), ref)
     img.free(); e.free()
     # cfg4: 8192x8192 RGB box / binomial blur (uint8 out).  Device layout: rows 128-byte aligned like every device copy the host entry
     # points make (conv_tma.cuh: tensor-map copies); the reference's dense (cols+K-1)*3 pitch (conv_sep.cuh) is timed beside it.
@@ -819,6 +866,10 @@ def other_kernels(pkg, L, peak, with_cpu=True):
     src = pkg.DeviceBuffer(rows * cols * 3); sums = pkg.DeviceBuffer(64)
     pkg.synth_dev(src, src.nbytes, 5); sums.fill(0)
     out["channel_sums_8192x8192"] = entry(rows * cols, 3, timeit(lambda: L.ompimg_channel_sums_dev(src.ptr, cols * 3, rows, cols, sums.ptr, 0)))
+    if O:                                            # the 13 launches accumulated onto the same three sums
+        ref = O.synth(rows * cols * 3, 5).reshape(-1, 3).sum(axis=0, dtype=np.uint64)
+        got = np.frombuffer(sums.download(24).tobytes(), np.uint64)
+        out["channel_sums_8192x8192"]["equals_oracle"] = bool((got == 13 * ref).all())
     src.free(); sums.free()
     pkg.sync()
     return out
